@@ -1,0 +1,35 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def load_fixture(name):
+    """tests/golden/<name>.npz -> (meta dict, arrays dict); see oracle/make_golden.py."""
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    meta = json.loads(str(z['meta']))
+    return meta, {k: z[k] for k in z.files if k != 'meta'}
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+
+
+@pytest.fixture(scope='session')
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return 0
