@@ -1,0 +1,862 @@
+// fib_capi.cu -- implementation of include/fib_b200.h (the C ABI of libfibb200.so).
+// Owns device memory (SoA fp32 planes), the stream / events / CUDA graphs, the step schedule of
+// every model and the halo exchange.  sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fib_b200.h"
+#include "model_br.cuh"
+#include "model_court.cuh"
+#include "model_fenton.cuh"
+
+using namespace fib;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(FIB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the library has no link-time dependency on libnccl)
+// ------------------------------------------------------------------------------------------
+struct Uid { char bytes[128]; };   // ncclUniqueId
+struct Nccl {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Uid /*by value*/, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char* names[] = {getenv("FIB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(FIB_E_NCCL, "cannot dlopen libnccl.so.2 (%s)", dlerror());
+#define SYM(field, name)                                                          \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                      \
+  if (!g_nccl.field) return fail(FIB_E_NCCL, "libnccl lacks symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.h = h;
+  return 0;
+}
+#define NC(call)                                                                             \
+  do {                                                                                       \
+    int r_ = (call);                                                                         \
+    if (r_ != 0) return fail(FIB_E_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+static const int kNcclFloat = 7;   // ncclFloat32
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static const char* kFentonVars[] = {"U", "V", "W", "S"};
+static const char* kBrVars[] = {"V", "C", "M", "H", "J", "D", "F", "XI"};
+static const char* kCourtVars[] = {"V", "_Na_i_", "_m_", "_h_", "_j_", "_K_i_", "_oa_", "_oi_",
+                                   "_ua_", "_ui_", "_xr_", "_xs_", "_Ca_i_", "_d_", "_f_", "_f_Ca_",
+                                   "_Ca_rel_", "_u_", "_v_", "_w_", "_Ca_up_", "_us_"};
+
+struct GraphKey { int op, cur; cudaGraphExec_t exec; };
+
+struct fib_ctx {
+  fib_config cfg;
+  Geom g;
+  int nvars = 0, dt_per_step = 1, sms = 148;
+  const char** names = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_bnd = nullptr, ev_comm = nullptr,
+              ev_group = nullptr;
+  float* x[2] = {nullptr, nullptr};   // diffusing variable, ping-pong, halo layout
+  int cur = 0;
+  float* s[S_COUNT] = {nullptr};      // other planes
+  float* phase = nullptr;             // halo layout
+  float* lut = nullptr;               // 150 x 30
+  bool have_lut = false, have_cheb = false, halo_dirty = true, comm_pending = false;
+  float cheb[12][9];
+  uint64_t launches = 0;
+  std::vector<GraphKey> graphs;
+  double* red = nullptr;              // 2 doubles for reductions
+  // NCCL
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  size_t plane_floats() const { return (size_t)g.rows * g.pitch; }
+  size_t halo_floats() const { return (size_t)(g.rows + 2) * g.pitch; }
+  bool top_is_border() const { return g.row0 == 0; }
+  bool bottom_is_border() const { return g.row0 + g.rows == g.H; }
+};
+
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+// ionic.py:144-163: X := max(X, s) with s = value inside the rectangle and floor_v elsewhere.
+// (m > x ? m : x) keeps a NaN in x, like tf.maximum.
+__global__ void stim_kernel(float* __restrict__ x, Geom g, int halo, int r0, int r1, int c0, int c1,
+                            float value, float floor_v) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lr = blockIdx.y;
+  if (c >= g.W || lr >= g.rows) return;
+  const int gr = g.row0 + lr;
+  const float m = (gr >= r0 && gr < r1 && c >= c0 && c < c1) ? value : floor_v;
+  float* p = x + (size_t)(lr + halo) * g.pitch + c;
+  const float v = *p;
+  *p = m > v ? m : v;
+}
+
+__global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict__ w, Geom g,
+                            int xhalo, double* out) {
+  double sx = 0.0, sw = 0.0;
+  for (int lr = blockIdx.x; lr < g.rows; lr += gridDim.x)
+    for (int c = threadIdx.x; c < g.W; c += blockDim.x) {
+      const double wv = w ? (double)w[(size_t)(lr + 1) * g.pitch + c] : 1.0;
+      sx += wv * (double)x[(size_t)(lr + xhalo) * g.pitch + c];
+      sw += wv;
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_down_sync(0xffffffffu, sx, o);
+    sw += __shfl_down_sync(0xffffffffu, sw, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, sx); atomicAdd(out + 1, sw); }
+}
+
+__global__ void court_inter_kernel(const float* __restrict__ v, int n, float* __restrict__ out,
+                                   int ncols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float q[kInterCols];
+  court_inter_dev<true>(v[i], q);
+  for (int k = 0; k < ncols; ++k) out[(size_t)i * ncols + k] = q[k];
+}
+
+__global__ void court_lut_kernel(float* __restrict__ lut) {   // courtemanche.h:473-479
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLutRows) return;
+  float q[kInterCols];
+  court_inter_dev<false>(static_cast<float>(i - 100), q);
+  for (int k = 0; k < kLutCols; ++k) lut[i * kLutCols + k] = q[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+extern "C" int fib_version(void) { return FIB_ABI_VERSION; }
+extern "C" const char* fib_last_error(void) { return g_err.c_str(); }
+extern "C" int fib_device_count(int* count) {
+  if (!count) return fail(FIB_E_ARG, "count is NULL");
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+extern "C" int fib_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(FIB_E_ARG, "out is NULL");
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int fib_host_free(void* p) {
+  CU(cudaFreeHost(p));
+  return 0;
+}
+
+extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
+  if (!cfg || !out) return fail(FIB_E_ARG, "cfg/out is NULL");
+  if (cfg->struct_size != sizeof(fib_config))
+    return fail(FIB_E_ARG, "fib_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size,
+                sizeof(fib_config));
+  if (cfg->model < FIB_FENTON4V || cfg->model > FIB_COURT_ULTRA)
+    return fail(FIB_E_ARG, "unknown model id %d", cfg->model);
+  if (cfg->height < 3 || cfg->width < 3)
+    return fail(FIB_E_ARG, "grid %dx%d too small: the two-stage boundary needs >= 3x3", cfg->height,
+                cfg->width);
+  if (!(cfg->dt > 0.0)) return fail(FIB_E_ARG, "dt must be > 0");
+  if (cfg->steps_per_launch > 1)
+    return fail(FIB_E_ARG, "steps_per_launch=%d: temporal blocking is not available in this build",
+                cfg->steps_per_launch);
+  int rows = cfg->rows == 0 ? cfg->height : cfg->rows;
+  int row0 = cfg->rows == 0 ? 0 : cfg->row0;
+  if (row0 < 0 || rows < 1 || row0 + rows > cfg->height)
+    return fail(FIB_E_ARG, "shard rows [%d,%d) outside the grid of height %d", row0, row0 + rows,
+                cfg->height);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(FIB_E_CUDA, "device %d not available (%d CUDA devices)", cfg->device, ndev);
+  DevGuard dg(cfg->device);
+
+  fib_ctx* c = new fib_ctx();
+  c->cfg = *cfg;
+  c->g.H = cfg->height;
+  c->g.W = cfg->width;
+  c->g.row0 = row0;
+  c->g.rows = rows;
+  c->g.pitch = (cfg->width + 31) / 32 * 32;
+  switch (cfg->model) {
+    case FIB_FENTON4V: c->nvars = 4; c->dt_per_step = 10; c->names = kFentonVars; break;
+    case FIB_BR: c->nvars = 8; c->dt_per_step = 5; c->names = kBrVars; break;
+    case FIB_COURT: c->nvars = 21; c->dt_per_step = 1; c->names = kCourtVars; break;
+    default:
+      c->nvars = (cfg->flags & FIB_F_ULTRA_SLOW) ? 22 : 21;
+      c->dt_per_step = 1;
+      c->names = kCourtVars;
+  }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  c->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev_start));
+  CU(cudaEventCreate(&c->ev_stop));
+  CU(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_group, cudaEventDisableTiming));
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaMalloc(&c->x[b], c->halo_floats() * sizeof(float)));
+    CU(cudaMemsetAsync(c->x[b], 0, c->halo_floats() * sizeof(float), c->stream));
+  }
+  for (int k = 0; k + 1 < c->nvars; ++k) {
+    CU(cudaMalloc(&c->s[k], c->plane_floats() * sizeof(float)));
+    CU(cudaMemsetAsync(c->s[k], 0, c->plane_floats() * sizeof(float), c->stream));
+  }
+  CU(cudaMalloc(&c->red, 2 * sizeof(double)));
+  if (cfg->model >= FIB_COURT) CU(cudaMalloc(&c->lut, sizeof(float) * kLutRows * kLutCols));
+  memset(c->cheb, 0, sizeof c->cheb);
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+extern "C" int fib_destroy(fib_ctx* c) {
+  if (!c) return 0;
+  DevGuard dg(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->comm_stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
+  for (int b = 0; b < 2; ++b) cudaFree(c->x[b]);
+  for (int k = 0; k < S_COUNT; ++k) cudaFree(c->s[k]);
+  cudaFree(c->phase);
+  cudaFree(c->lut);
+  cudaFree(c->red);
+  cudaEventDestroy(c->ev_start);
+  cudaEventDestroy(c->ev_stop);
+  cudaEventDestroy(c->ev_bnd);
+  cudaEventDestroy(c->ev_comm);
+  cudaEventDestroy(c->ev_group);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->comm_stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int fib_num_vars(const fib_ctx* c) { return c ? c->nvars : fail(FIB_E_ARG, "ctx is NULL"); }
+extern "C" const char* fib_var_name(const fib_ctx* c, int var) {
+  return (c && var >= 0 && var < c->nvars) ? c->names[var] : nullptr;
+}
+extern "C" int fib_var_index(const fib_ctx* c, const char* name) {
+  if (!c || !name) return fail(FIB_E_ARG, "ctx/name is NULL");
+  for (int i = 0; i < c->nvars; ++i)
+    if (!strcmp(c->names[i], name)) return i;
+  return fail(FIB_E_ARG, "unknown state variable '%s'", name);
+}
+extern "C" int fib_dt_per_step(const fib_ctx* c) { return c ? c->dt_per_step : fail(FIB_E_ARG, "ctx is NULL"); }
+
+// plane base pointer of the first OWNED row + whether the plane is in halo layout
+static float* owned_rows(fib_ctx* c, int var) {
+  return var == 0 ? c->x[c->cur] + c->g.pitch : c->s[var - 1];
+}
+
+extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
+  if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (n != (size_t)c->g.rows * c->g.W)
+    return fail(FIB_E_ARG, "fib_set_state: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemcpy2DAsync(owned_rows(c, var), c->g.pitch * sizeof(float), host, c->g.W * sizeof(float),
+                       c->g.W * sizeof(float), c->g.rows, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (var == 0) c->halo_dirty = true;
+  return 0;
+}
+
+extern "C" int fib_get_state(fib_ctx* c, int var, float* host, size_t n) {
+  if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (n != (size_t)c->g.rows * c->g.W)
+    return fail(FIB_E_ARG, "fib_get_state: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemcpy2DAsync(host, c->g.W * sizeof(float), owned_rows(c, var), c->g.pitch * sizeof(float),
+                       c->g.W * sizeof(float), c->g.rows, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_get_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1, float* host) {
+  if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
+    return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
+  DevGuard dg(c->cfg.device);
+  const float* src = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch + c0;
+  CU(cudaMemcpy2DAsync(host, (size_t)(c1 - c0) * sizeof(float), src, c->g.pitch * sizeof(float),
+                       (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  CU(cudaStreamSynchronize(c->stream));
+  for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);   // graphs bake the phase pointer in
+  c->graphs.clear();
+  if (!rows_host) {
+    CU(cudaFree(c->phase));
+    c->phase = nullptr;
+    return 0;
+  }
+  const int need0 = max(c->g.row0 - 1, 0), need1 = min(c->g.row0 + c->g.rows + 1, c->g.H);
+  if (first_row > need0 || first_row + nrows < need1)
+    return fail(FIB_E_ARG, "phase rows [%d,%d) do not cover [%d,%d)", first_row, first_row + nrows,
+                need0, need1);
+  if (!c->phase) {
+    CU(cudaMalloc(&c->phase, c->halo_floats() * sizeof(float)));
+    CU(cudaMemsetAsync(c->phase, 0, c->halo_floats() * sizeof(float), c->stream));
+  }
+  // device row (need0 - row0 + 1) <- host row (need0 - first_row)
+  CU(cudaMemcpy2DAsync(c->phase + (size_t)(need0 - c->g.row0 + 1) * c->g.pitch,
+                       c->g.pitch * sizeof(float),
+                       rows_host + (size_t)(need0 - first_row) * c->g.W, c->g.W * sizeof(float),
+                       c->g.W * sizeof(float), need1 - need0, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_set_table(fib_ctx* c, int table, const float* data, size_t n) {
+  if (!c || !data) return fail(FIB_E_ARG, "ctx/data is NULL");
+  DevGuard dg(c->cfg.device);
+  if (table == FIB_TABLE_BR_CHEBY) {
+    if (n != 12 * 9) return fail(FIB_E_ARG, "BR Chebyshev table must hold 12*9 floats, got %zu", n);
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(c->cheb, data, sizeof c->cheb);
+    c->have_cheb = true;
+    for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
+    c->graphs.clear();
+    return 0;
+  }
+  if (table == FIB_TABLE_COURT_LUT) {
+    if (!c->lut) return fail(FIB_E_STATE, "this model has no lookup table");
+    if (n != (size_t)kLutRows * kLutCols)
+      return fail(FIB_E_ARG, "Courtemanche LUT must hold 150*30 floats, got %zu", n);
+    CU(cudaMemcpyAsync(c->lut, data, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_lut = true;
+    return 0;
+  }
+  return fail(FIB_E_ARG, "unknown table id %d", table);
+}
+
+extern "C" int fib_get_table(fib_ctx* c, int table, float* data, size_t n) {
+  if (!c || !data) return fail(FIB_E_ARG, "ctx/data is NULL");
+  DevGuard dg(c->cfg.device);
+  if (table == FIB_TABLE_BR_CHEBY) {
+    if (n != 12 * 9) return fail(FIB_E_ARG, "BR Chebyshev table holds 12*9 floats");
+    memcpy(data, c->cheb, sizeof c->cheb);
+    return 0;
+  }
+  if (table == FIB_TABLE_COURT_LUT) {
+    if (!c->lut || !c->have_lut) return fail(FIB_E_STATE, "no lookup table has been set or built");
+    if (n != (size_t)kLutRows * kLutCols) return fail(FIB_E_ARG, "Courtemanche LUT holds 150*30 floats");
+    CU(cudaMemcpyAsync(data, c->lut, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  return fail(FIB_E_ARG, "unknown table id %d", table);
+}
+
+extern "C" int fib_build_lut(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (!c->lut) return fail(FIB_E_STATE, "this model has no lookup table");
+  DevGuard dg(c->cfg.device);
+  court_lut_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut);
+  CU(cudaGetLastError());
+  c->launches++;
+  c->have_lut = true;
+  return 0;
+}
+
+extern "C" int fib_court_inter(fib_ctx* c, const float* v_host, size_t n, float* out_host) {
+  if (!c || !v_host || !out_host) return fail(FIB_E_ARG, "NULL argument");
+  if (n == 0) return 0;
+  DevGuard dg(c->cfg.device);
+  float *dv = nullptr, *dq = nullptr;
+  CU(cudaMalloc(&dv, n * sizeof(float)));
+  CU(cudaMalloc(&dq, n * kInterCols * sizeof(float)));
+  CU(cudaMemcpyAsync(dv, v_host, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  court_inter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dv, (int)n, dq, kInterCols);
+  CU(cudaGetLastError());
+  c->launches++;
+  CU(cudaMemcpyAsync(out_host, dq, n * kInterCols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(dv);
+  cudaFree(dq);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// the step schedule
+// ------------------------------------------------------------------------------------------
+static int substeps_of(const fib_ctx* c, int op) {
+  if (op == FIB_OP_ODE) return c->dt_per_step;
+  return c->cfg.model == FIB_COURT ? 1 : 0;   // 'slow' is an empty group elsewhere
+}
+
+template <class M>
+static void fill_common(fib_ctx* c, StepArgs<M>& a, int lr0, int nrows) {
+  a.xin = c->x[c->cur];
+  a.xout = c->x[c->cur ^ 1];
+  for (int k = 0; k < M::NS; ++k) a.s[k] = c->s[k];
+  a.phase = c->phase;
+  a.lut = c->lut;
+  a.lr0 = lr0;
+  a.nrows = nrows;
+}
+
+template <int MODE, bool LUT, bool US>
+static cudaError_t launch_court(fib_ctx* c, int lr0, int nrows) {
+  using M = Courtemanche<MODE, LUT, US>;
+  StepArgs<M> a;
+  fill_common<M>(c, a, lr0, nrows);
+  const double dt = c->cfg.dt;
+  const double dts = (c->cfg.model == FIB_COURT) ? dt * 10 : dt;   // court.py:118-122
+  const double chron = (c->cfg.flags & FIB_F_NO_CHRONIC) ? 0.0 : 1.0;
+  a.p.dt_fast = (float)dt;
+  a.p.neg_dt_fast = (float)(-dt);
+  a.p.dt_slow = (float)dts;
+  a.p.neg_dt_slow = (float)(-dts);
+  a.p.ddt = (float)(c->cfg.diff * dt);
+  a.p.e_fCa = (float)expm1((double)(float)(-dts / 2.0));
+  a.p.e_u = (float)expm1((double)(float)(-dts / 8.0));
+  a.p.k_to = (float)((1.0 - 0.5 * chron) * 100 * 0.1652);
+  a.p.k_Kur = (float)((1.0 - 0.5 * chron) * 100);
+  a.p.k_CaL = (float)((1.0 - 0.7 * chron) * 100 * 0.12375);
+  return launch_step<M>(c->g, a, c->stream, c->sms);
+}
+
+// One time step `sub` of op over local rows [lr0, lr0+nrows).  Does NOT flip the ping-pong.
+static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
+  if (nrows <= 0) return 0;
+  const double dt = c->cfg.dt;
+  const uint32_t fl = c->cfg.flags;
+  cudaError_t e = cudaSuccess;
+  switch (c->cfg.model) {
+    case FIB_FENTON4V: {
+      StepArgs<Fenton4v> a;
+      fill_common<Fenton4v>(c, a, lr0, nrows);
+      a.p.dt = (float)dt;
+      a.p.ddt = (float)(c->cfg.diff * dt);
+      e = launch_step<Fenton4v>(c->g, a, c->stream, c->sms);
+      break;
+    }
+    case FIB_BR: {
+      // br.py:96-107: skip -> solve(n=5) then 4x solve(n=0); else 5x solve(n=1)
+      const int n = (fl & FIB_F_SKIP) ? (sub == 0 ? 5 : 0) : 1;
+      const bool cheby = fl & FIB_F_CHEBY;
+      if (cheby && !c->have_cheb)
+        return fail(FIB_E_STATE, "cheby=True but FIB_TABLE_BR_CHEBY has not been set");
+      auto go = [&](auto tag) {
+        using M = decltype(tag);
+        StepArgs<M> a;
+        fill_common<M>(c, a, lr0, nrows);
+        a.p.dt = (float)dt;
+        a.p.neg_dt = (float)(-dt);
+        a.p.neg_dt_slow = (float)(-(dt * n));
+        a.p.ddt = (float)(c->cfg.diff * dt);
+        memcpy(a.p.cheb, c->cheb, sizeof c->cheb);
+        return launch_step<M>(c->g, a, c->stream, c->sms);
+      };
+      if (cheby) e = n > 0 ? go(BeelerReuter<true, true>()) : go(BeelerReuter<true, false>());
+      else       e = n > 0 ? go(BeelerReuter<false, true>()) : go(BeelerReuter<false, false>());
+      break;
+    }
+    case FIB_COURT: {
+      const bool lut = fl & FIB_F_LUT;
+      if (lut && !c->have_lut) return fail(FIB_E_STATE, "lut=True but no table was set/built");
+      if (op == FIB_OP_ODE) e = lut ? launch_court<COURT_FAST, true, false>(c, lr0, nrows)
+                                    : launch_court<COURT_FAST, false, false>(c, lr0, nrows);
+      else                  e = lut ? launch_court<COURT_SLOW, true, false>(c, lr0, nrows)
+                                    : launch_court<COURT_SLOW, false, false>(c, lr0, nrows);
+      break;
+    }
+    default: {
+      const bool lut = fl & FIB_F_LUT, us = fl & FIB_F_ULTRA_SLOW;
+      if (lut && !c->have_lut) return fail(FIB_E_STATE, "lut=True but no table was set/built");
+      if (us) e = lut ? launch_court<COURT_ALL, true, true>(c, lr0, nrows)
+                      : launch_court<COURT_ALL, false, true>(c, lr0, nrows);
+      else    e = lut ? launch_court<COURT_ALL, true, false>(c, lr0, nrows)
+                      : launch_court<COURT_ALL, false, false>(c, lr0, nrows);
+    }
+  }
+  if (e != cudaSuccess) return fail(FIB_E_CUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+  c->launches++;
+  return 0;
+}
+
+static bool op_writes_x(const fib_ctx* c, int op) { return !(c->cfg.model == FIB_COURT && op == FIB_OP_SLOW); }
+
+// ---- NCCL halo exchange of buffer `buf` (rows just written), on `st` ------------------------
+static int nccl_exchange(fib_ctx* c, float* buf, cudaStream_t st) {
+  const size_t W = c->g.W, P = c->g.pitch;
+  NC(g_nccl.GroupStart());
+  if (c->rank > 0) {
+    NC(g_nccl.Send(buf + P, W, kNcclFloat, c->rank - 1, c->comm, st));
+    NC(g_nccl.Recv(buf, W, kNcclFloat, c->rank - 1, c->comm, st));
+  }
+  if (c->rank + 1 < c->nranks) {
+    NC(g_nccl.Send(buf + (size_t)c->g.rows * P, W, kNcclFloat, c->rank + 1, c->comm, st));
+    NC(g_nccl.Recv(buf + (size_t)(c->g.rows + 1) * P, W, kNcclFloat, c->rank + 1, c->comm, st));
+  }
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+static int run_iteration_plain(fib_ctx* c, int op) {
+  const int ns = substeps_of(c, op);
+  for (int s = 0; s < ns; ++s) {
+    int r = launch_substep(c, op, s, 0, c->g.rows);
+    if (r) return r;
+    if (op_writes_x(c, op)) c->cur ^= 1;
+  }
+  return 0;
+}
+
+// boundary rows first, halo exchange on the side stream overlapped with the interior rows
+static int run_iteration_nccl(fib_ctx* c, int op) {
+  const int ns = substeps_of(c, op);
+  const int rows = c->g.rows;
+  for (int s = 0; s < ns; ++s) {
+    if (!op_writes_x(c, op)) {
+      int r = launch_substep(c, op, s, 0, rows);
+      if (r) return r;
+      continue;
+    }
+    if (c->comm_pending) {   // halos of x[cur] must have arrived
+      CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+      c->comm_pending = false;
+    }
+    int r;
+    if (rows >= 3) {
+      if ((r = launch_substep(c, op, s, 0, 1))) return r;
+      if ((r = launch_substep(c, op, s, rows - 1, 1))) return r;
+      CU(cudaEventRecord(c->ev_bnd, c->stream));
+      CU(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+      if ((r = nccl_exchange(c, c->x[c->cur ^ 1], c->comm_stream))) return r;
+      CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+      c->comm_pending = true;
+      if ((r = launch_substep(c, op, s, 1, rows - 2))) return r;
+    } else {
+      if ((r = launch_substep(c, op, s, 0, rows))) return r;
+      if ((r = nccl_exchange(c, c->x[c->cur ^ 1], c->stream))) return r;
+    }
+    c->cur ^= 1;
+  }
+  return 0;
+}
+
+static int refresh_halos_nccl(fib_ctx* c) {
+  if (!c->halo_dirty) return 0;
+  int r = nccl_exchange(c, c->x[c->cur], c->stream);
+  if (r) return r;
+  c->halo_dirty = false;
+  return 0;
+}
+
+extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (op != FIB_OP_ODE && op != FIB_OP_SLOW) return fail(FIB_E_ARG, "unknown op %d", op);
+  if (n_iter < 0) return fail(FIB_E_ARG, "n_iter < 0");
+  if (substeps_of(c, op) == 0 || n_iter == 0) return 0;
+  DevGuard dg(c->cfg.device);
+  if (c->comm) {
+    int r = refresh_halos_nccl(c);
+    if (r) return r;
+    for (int i = 0; i < n_iter; ++i)
+      if ((r = run_iteration_nccl(c, op))) return r;
+    return 0;
+  }
+  if (c->g.rows != c->g.H)
+    return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
+  if (c->cfg.flags & FIB_F_NO_GRAPH) {
+    for (int i = 0; i < n_iter; ++i) {
+      int r = run_iteration_plain(c, op);
+      if (r) return r;
+    }
+    return 0;
+  }
+  // CUDA graph of one iteration, cached per (op, ping-pong parity)
+  for (int i = 0; i < n_iter; ++i) {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& gk : c->graphs)
+      if (gk.op == op && gk.cur == c->cur) exec = gk.exec;
+    const int cur0 = c->cur;
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const uint64_t l0 = c->launches;
+      int r = run_iteration_plain(c, op);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      c->launches = l0;
+      c->cur = cur0;
+      if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce != cudaSuccess) return fail(FIB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      CU(cudaGraphInstantiate(&exec, graph, 0));
+      CU(cudaGraphDestroy(graph));
+      c->graphs.push_back({op, cur0, exec});
+    }
+    CU(cudaGraphLaunch(exec, c->stream));
+    const int ns = substeps_of(c, op);
+    c->launches += ns;
+    if (op_writes_x(c, op) && (ns & 1)) c->cur ^= 1;
+  }
+  return 0;
+}
+
+// ---- in-process shard group: lock-step, device-to-device halo copies ------------------------
+static int group_copy_halos(fib_ctx** cs, int n, bool written_buffer) {
+  // copies the boundary rows of buffer (cur^1 if written_buffer else cur) into the neighbours'
+  // halo rows, each on the SOURCE stream, then records ev_group on every stream.
+  for (int i = 0; i < n; ++i) {
+    fib_ctx* c = cs[i];
+    DevGuard dg(c->cfg.device);
+    const int b = written_buffer ? (c->cur ^ 1) : c->cur;
+    const size_t P = c->g.pitch, Wb = c->g.W * sizeof(float);
+    if (i > 0) {
+      fib_ctx* up = cs[i - 1];
+      const int ub = written_buffer ? (up->cur ^ 1) : up->cur;
+      CU(cudaMemcpyPeerAsync(up->x[ub] + (size_t)(up->g.rows + 1) * up->g.pitch, up->cfg.device,
+                             c->x[b] + P, c->cfg.device, Wb, c->stream));
+    }
+    if (i + 1 < n) {
+      fib_ctx* dn = cs[i + 1];
+      const int db = written_buffer ? (dn->cur ^ 1) : dn->cur;
+      CU(cudaMemcpyPeerAsync(dn->x[db], dn->cfg.device, c->x[b] + (size_t)c->g.rows * P,
+                             c->cfg.device, Wb, c->stream));
+    }
+    CU(cudaEventRecord(c->ev_group, c->stream));
+  }
+  return 0;
+}
+
+static int group_wait_neighbours(fib_ctx** cs, int n) {
+  for (int i = 0; i < n; ++i) {
+    DevGuard dg(cs[i]->cfg.device);
+    if (i > 0) CU(cudaStreamWaitEvent(cs[i]->stream, cs[i - 1]->ev_group, 0));
+    if (i + 1 < n) CU(cudaStreamWaitEvent(cs[i]->stream, cs[i + 1]->ev_group, 0));
+  }
+  return 0;
+}
+
+extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
+  if (!cs || n < 1) return fail(FIB_E_ARG, "empty shard group");
+  if (op != FIB_OP_ODE && op != FIB_OP_SLOW) return fail(FIB_E_ARG, "unknown op %d", op);
+  int row = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!cs[i]) return fail(FIB_E_ARG, "shard %d is NULL", i);
+    if (cs[i]->g.row0 != row || cs[i]->g.H != cs[0]->g.H || cs[i]->g.W != cs[0]->g.W ||
+        cs[i]->cfg.model != cs[0]->cfg.model || cs[i]->cfg.flags != cs[0]->cfg.flags)
+      return fail(FIB_E_ARG, "shard %d is not the row-adjacent continuation of shard %d", i, i - 1);
+    row += cs[i]->g.rows;
+  }
+  if (row != cs[0]->g.H) return fail(FIB_E_ARG, "shards cover %d of %d rows", row, cs[0]->g.H);
+  const int ns = substeps_of(cs[0], op);
+  if (ns == 0 || n_iter == 0) return 0;
+  int r;
+  bool dirty = false;
+  for (int i = 0; i < n; ++i) dirty |= cs[i]->halo_dirty;
+  if (dirty) {
+    if ((r = group_copy_halos(cs, n, false))) return r;
+    if ((r = group_wait_neighbours(cs, n))) return r;
+    for (int i = 0; i < n; ++i) cs[i]->halo_dirty = false;
+  }
+  for (int it = 0; it < n_iter; ++it)
+    for (int s = 0; s < ns; ++s) {
+      for (int i = 0; i < n; ++i) {
+        DevGuard dg(cs[i]->cfg.device);
+        if ((r = launch_substep(cs[i], op, s, 0, cs[i]->g.rows))) return r;
+      }
+      if (op_writes_x(cs[0], op)) {
+        if ((r = group_copy_halos(cs, n, true))) return r;
+        if ((r = group_wait_neighbours(cs, n))) return r;
+        for (int i = 0; i < n; ++i) cs[i]->cur ^= 1;
+      }
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stimulus, probes, reductions
+// ------------------------------------------------------------------------------------------
+extern "C" int fib_stimulate(fib_ctx* c, int var, int r0, int r1, int c0, int c1, float value,
+                             float floor_v) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  DevGuard dg(c->cfg.device);
+  if (c->comm_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+    c->comm_pending = false;
+  }
+  dim3 block(128), grid((c->g.W + 127) / 128, c->g.rows);
+  float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
+  stim_kernel<<<grid, block, 0, c->stream>>>(base, c->g, var == 0 ? 1 : 0, r0, r1, c0, c1, value, floor_v);
+  CU(cudaGetLastError());
+  c->launches++;
+  if (var == 0) c->halo_dirty = true;
+  return 0;
+}
+
+extern "C" int fib_probe(fib_ctx* c, int var, int row, int col, float* out) {
+  if (!c || !out) return fail(FIB_E_ARG, "ctx/out is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (row < c->g.row0 || row >= c->g.row0 + c->g.rows || col < 0 || col >= c->g.W)
+    return fail(FIB_E_ARG, "probe (%d,%d) is not in this shard", row, col);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemcpyAsync(out, owned_rows(c, var) + (size_t)(row - c->g.row0) * c->g.pitch + col,
+                     sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_weighted_sum(fib_ctx* c, int var, double* sum_wx, double* sum_w) {
+  if (!c || !sum_wx || !sum_w) return fail(FIB_E_ARG, "NULL argument");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
+  const float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
+  wsum_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(base, c->phase, c->g, var == 0 ? 1 : 0, c->red);
+  CU(cudaGetLastError());
+  c->launches++;
+  double h[2];
+  CU(cudaMemcpyAsync(h, c->red, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *sum_wx = h[0];
+  *sum_w = h[1];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sync / timing
+// ------------------------------------------------------------------------------------------
+extern "C" int fib_sync(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->comm_stream));
+  return 0;
+}
+extern "C" int fib_timer_start(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  CU(cudaEventRecord(c->ev_start, c->stream));
+  return 0;
+}
+extern "C" int fib_timer_stop(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  if (c->comm_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  CU(cudaEventRecord(c->ev_stop, c->stream));
+  return 0;
+}
+extern "C" int fib_timer_ms(fib_ctx* c, float* ms) {
+  if (!c || !ms) return fail(FIB_E_ARG, "ctx/ms is NULL");
+  DevGuard dg(c->cfg.device);
+  CU(cudaEventSynchronize(c->ev_stop));
+  CU(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+  return 0;
+}
+extern "C" int fib_launch_count(const fib_ctx* c, uint64_t* kernels) {
+  if (!c || !kernels) return fail(FIB_E_ARG, "ctx/kernels is NULL");
+  *kernels = c->launches;
+  return 0;
+}
+extern "C" int fib_stream(const fib_ctx* c, void** cuda_stream) {
+  if (!c || !cuda_stream) return fail(FIB_E_ARG, "ctx/out is NULL");
+  *cuda_stream = (void*)c->stream;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-process sharding
+// ------------------------------------------------------------------------------------------
+extern "C" int fib_comm_unique_id(void* out128) {
+  if (!out128) return fail(FIB_E_ARG, "out128 is NULL");
+  int r = nccl_load();
+  if (r) return r;
+  NC(g_nccl.GetUniqueId(out128));
+  return 0;
+}
+
+extern "C" int fib_comm_init(fib_ctx* c, int nranks, int rank, const void* id128) {
+  if (!c || !id128) return fail(FIB_E_ARG, "ctx/id is NULL");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(FIB_E_ARG, "bad rank %d of %d", rank, nranks);
+  if (c->comm) return fail(FIB_E_STATE, "communicator already initialised");
+  if (nranks == 1) return 0;   // a single shard needs no communicator
+  if ((rank == 0) != c->top_is_border() || (rank == nranks - 1) != c->bottom_is_border())
+    return fail(FIB_E_ARG, "rank %d of %d does not match shard rows [%d,%d) of %d", rank, nranks,
+                c->g.row0, c->g.row0 + c->g.rows, c->g.H);
+  int r = nccl_load();
+  if (r) return r;
+  DevGuard dg(c->cfg.device);
+  Uid uid;
+  memcpy(uid.bytes, id128, sizeof uid.bytes);
+  NC(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+  c->nranks = nranks;
+  c->rank = rank;
+  c->halo_dirty = true;
+  return 0;
+}

@@ -1,0 +1,59 @@
+// fib_common.cuh -- geometry, vector access and small math helpers shared by every kernel.
+// sm_100a only.  No CPU fallback exists anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fib {
+
+// Geometry of one shard.  Planes are SoA fp32, row pitch `pitch` floats (multiple of 32 -> every
+// row starts 128-B aligned, so float4 accesses are always legal and padded columns are in-bounds).
+// The diffusing variable and the phase field carry one halo row above and below the shard:
+//   diffusing/phase plane:  element (global row g, col c) = p[(g - row0 + 1) * pitch + c]
+//   every other plane:      element (global row g, col c) = p[(g - row0) * pitch + c]
+struct Geom {
+  int H, W;         // global grid (config 'height', 'width')
+  int row0, rows;   // this shard owns global rows [row0, row0+rows)
+  int pitch;        // floats per row
+};
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<1> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = *p; }
+  static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
+};
+template <> struct VecIO<2> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// tf.clip_by_value(x, lo, hi) == min(max(x, lo), hi) with NaN propagating (ionic.py:122-123,
+// br.py:167-168).  fminf/fmaxf would swallow a NaN; the reference does not.
+__device__ __forceinline__ float clip_nan(float x, float lo, float hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).
+// neg_dt = fp32(-dt) (or fp32(-(dt*n)) folded in double on the host, br.py:197-200).
+__device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, float neg_dt) {
+  float e = expm1f(neg_dt / tau);
+  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+}
+// same with e = expm1(-dt/tau) precomputed (Python-scalar tau: court.py:189,243)
+__device__ __forceinline__ float rush_larsen_e(float g, float g_inf, float e) {
+  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+}
+
+}  // namespace fib

@@ -1,0 +1,158 @@
+// fib_kernels.cuh -- the generic fused step kernel: one launch = one explicit time step of one
+// shard (or of a row range of it): boundary + Laplacian + phase term + pointwise ionic update.
+//
+// Work decomposition (HBM-bound stencil + pointwise ODEs; no tensor cores by design):
+//   * a thread owns VEC consecutive cells of a row (one 16-B access per plane for VEC=4) and
+//     MARCHES down R rows, keeping the 3-row window of the diffusing variable in registers, so
+//     each of its rows is fetched once per strip instead of three times;
+//   * a warp covers 32*VEC contiguous columns -> every plane access is a full 128-B line per
+//     4 lanes, perfectly coalesced; vertically adjacent warps of a CTA share the strip-edge rows
+//     through L1;
+//   * only the diffusing variable is ping-ponged (xin -> xout); every other plane is updated in
+//     place, so the algorithmic traffic is exactly one read + one write per state variable.
+#pragma once
+#include "fib_stencil.cuh"
+
+namespace fib {
+
+// A model M provides:
+//   NS            number of non-diffusing planes
+//   NEED_RAW      reaction term reads the un-enforced centre value (Fenton 4v, fenton.py:101)
+//   NEED_LAP      step needs the stencil (false for the Courtemanche 'slow' op)
+//   STORE_X       step writes the diffusing variable
+//   stores(k)     plane k is written by this step
+//   struct Params (uniform scalars / small tables; lives in the kernel parameter bank)
+//   cell(p, xraw, x0, lap, s[NS], xnew)
+template <class M>
+struct StepArgs {
+  const float* xin;              // diffusing variable, halo layout
+  float* xout;                   // ping-pong target (halo layout)
+  float* s[M::NS > 0 ? M::NS : 1];  // non-diffusing planes (in place)
+  const float* phase;            // halo layout, or nullptr
+  const float* lut;              // Courtemanche 150x30 table (global), or nullptr
+  int lr0, nrows;                // local row range [lr0, lr0+nrows) processed by this launch
+  typename M::Params p;
+};
+
+constexpr int kBX = 32;   // threads along columns (one warp)
+
+template <class M, int VEC, int R, int BY, bool PHASE>
+__global__ void __launch_bounds__(kBX* BY)
+step_kernel(const Geom g, const StepArgs<M> a) {
+  M::prologue(a);   // e.g. stage the Courtemanche LUT in shared memory
+  const int c = (blockIdx.x * kBX + threadIdx.x) * VEC;
+  const int strip = blockIdx.y * BY + threadIdx.y;
+  const int gr0 = g.row0 + a.lr0 + strip * R;                 // first global row of my strip
+  const int gend = min(gr0 + R, g.row0 + a.lr0 + a.nrows);    // one past my last row
+  if (c >= g.W || gr0 >= gend) return;
+
+  const size_t pitch = g.pitch;
+  const bool col_edge = !(c >= 2 && c + VEC <= g.W - 2);
+
+  float xN[VEC + 2], xC[VEC + 2], xS[VEC + 2];
+  float pN[VEC + 2], pC[VEC + 2], pS[VEC + 2];   // phase-field window (REFLECT padding)
+  if (M::NEED_LAP) {
+    load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr0 - 1, 1, g.H - 2) - g.row0 + 1) * pitch, c,
+                           g.W, xN);
+    if (PHASE) {
+      load_reflect_row<VEC>(a.phase + (size_t)(reflecti(gr0 - 1, g.H) - g.row0 + 1) * pitch, c,
+                            g.W, pN);
+      load_reflect_row<VEC>(a.phase + (size_t)(gr0 - g.row0 + 1) * pitch, c, g.W, pC);
+    }
+  }
+  load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr0, 1, g.H - 2) - g.row0 + 1) * pitch, c, g.W,
+                         xC);
+
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int gr = gr0 + i;
+    if (gr < gend) {
+      if (M::NEED_LAP) {
+        load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr + 1, 1, g.H - 2) - g.row0 + 1) * pitch,
+                               c, g.W, xS);
+        if (PHASE)
+          load_reflect_row<VEC>(a.phase + (size_t)(reflecti(gr + 1, g.H) - g.row0 + 1) * pitch, c,
+                                g.W, pS);
+      }
+      // raw centre values: differ from the enforced ones only on the global border ring
+      float xraw[VEC];
+      if (M::NEED_RAW && (col_edge || gr == 0 || gr == g.H - 1)) {
+        VecIO<VEC>::ld(a.xin + (size_t)(gr - g.row0 + 1) * pitch + c, xraw);
+      } else {
+#pragma unroll
+        for (int l = 0; l < VEC; ++l) xraw[l] = xC[l + 1];
+      }
+      const size_t off = (size_t)(gr - g.row0) * pitch + c;
+      float sv[M::NS > 0 ? M::NS : 1][VEC];
+#pragma unroll
+      for (int k = 0; k < M::NS; ++k) VecIO<VEC>::ld(a.s[k] + off, sv[k]);
+
+      float xnew[VEC];
+#pragma unroll
+      for (int l = 0; l < VEC; ++l) {
+        float lap = 0.f;
+        if (M::NEED_LAP) {
+          lap = lap9(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], xN[l], xS[l], xN[l + 2], xS[l + 2],
+                     xC[l + 1]);
+          if (PHASE)
+            lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l + 1],
+                                            pS[l + 1], pC[l], pC[l + 2], pC[l + 1]));
+        }
+        float sl[M::NS > 0 ? M::NS : 1];
+#pragma unroll
+        for (int k = 0; k < M::NS; ++k) sl[k] = sv[k][l];
+        M::cell(a, xraw[l], xC[l + 1], lap, sl, xnew[l]);
+#pragma unroll
+        for (int k = 0; k < M::NS; ++k) sv[k][l] = sl[k];
+      }
+#pragma unroll
+      for (int k = 0; k < M::NS; ++k)
+        if (M::stores(k)) VecIO<VEC>::st(a.s[k] + off, sv[k]);
+      if (M::STORE_X) VecIO<VEC>::st(a.xout + (size_t)(gr - g.row0 + 1) * pitch + c, xnew);
+
+      if (M::NEED_LAP) {
+#pragma unroll
+        for (int j = 0; j < VEC + 2; ++j) { xN[j] = xC[j]; xC[j] = xS[j]; }
+        if (PHASE) {
+#pragma unroll
+          for (int j = 0; j < VEC + 2; ++j) { pN[j] = pC[j]; pC[j] = pS[j]; }
+        }
+      } else if (i + 1 < R && gr + 1 < gend) {
+        load_enforced_row<VEC>(
+            a.xin + (size_t)(clampi(gr + 1, 1, g.H - 2) - g.row0 + 1) * pitch, c, g.W, xC);
+      }
+    }
+  }
+}
+
+template <class M, int VEC, int R, int BY, bool PHASE>
+inline cudaError_t launch_step_r(const Geom& g, const StepArgs<M>& a, cudaStream_t st) {
+  const int ncg = (g.W + VEC - 1) / VEC;
+  dim3 block(kBX, BY);
+  dim3 grid((ncg + kBX - 1) / kBX, ((a.nrows + R - 1) / R + BY - 1) / BY);
+  step_kernel<M, VEC, R, BY, PHASE><<<grid, block, M::smem_bytes(), st>>>(g, a);
+  return cudaGetLastError();
+}
+
+// Picks the marching depth R: as deep as possible while the grid still has >= 4 CTAs per SM
+// (148 SMs); small grids (512^2) fall back to R = 1 and are launch-latency bound anyway.
+template <class M, int VEC, int BY, bool PHASE>
+inline cudaError_t launch_step_p(const Geom& g, const StepArgs<M>& a, cudaStream_t st, int sms) {
+  const int ncg = (g.W + VEC - 1) / VEC;
+  const long bx = (ncg + kBX - 1) / kBX;
+  auto blocks = [&](int R) { return bx * (((a.nrows + R - 1) / R + BY - 1) / BY); };
+  const long want = 4L * sms;
+  if (M::MAX_R >= 8 && blocks(8) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 8 ? 8 : 1), BY, PHASE>(g, a, st);
+  if (M::MAX_R >= 4 && blocks(4) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
+  if (M::MAX_R >= 2 && blocks(2) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);
+  return launch_step_r<M, VEC, 1, BY, PHASE>(g, a, st);
+}
+
+template <class M>
+inline cudaError_t launch_step(const Geom& g, const StepArgs<M>& a, cudaStream_t st, int sms) {
+  if (a.nrows <= 0) return cudaSuccess;
+  if (a.phase && M::NEED_LAP) return launch_step_p<M, M::VEC, M::BY, true>(g, a, st, sms);
+  return launch_step_p<M, M::VEC, M::BY, false>(g, a, st, sms);
+}
+
+}  // namespace fib

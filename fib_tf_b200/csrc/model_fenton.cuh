@@ -1,0 +1,60 @@
+// model_fenton.cuh -- Cherry-Ehrlich-Nattel-Fenton 4-variable model, pointwise part.
+// Restates fenton.py:46-92 (differentiate) and fenton.py:103-106 (explicit Euler).
+#pragma once
+#include "fib_kernels.cuh"
+
+namespace fib {
+
+struct Fenton4v {
+  static constexpr int NS = 3;            // V, W, S  (U is the diffusing variable)
+  static constexpr int VEC = 4;
+  static constexpr int BY = 4;
+  static constexpr int MAX_R = 8;
+  static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
+  static constexpr bool NEED_LAP = true;
+  static constexpr bool STORE_X = true;
+  static __host__ __device__ constexpr bool stores(int) { return true; }
+  static size_t smem_bytes() { return 0; }
+  struct Params {
+    float dt;    // fp32(dt)
+    float ddt;   // fp32(diff * dt), folded in double like the reference (fenton.py:103)
+  };
+  static __device__ __forceinline__ void prologue(const StepArgs<Fenton4v>&) {}
+
+  // Divisions by literals are multiplications by the correctly rounded reciprocal (<= 1 ulp from
+  // the reference's fp32 division; budgeted in SURVEY.md Appendix B.2).
+  static __device__ __forceinline__ void cell(const StepArgs<Fenton4v>& a, float U, float U0,
+                                              float lap, float (&s)[NS], float& Unew) {
+    constexpr float tau_vp = 3.33f, tau_vn = 19.2f, tau_wp = 160.0f, tau_wn = 75.0f;
+    constexpr float tau_d = 0.065f, tau_si = 31.8364f, tau_so = 31.8364f, tau_a = 0.009f;
+    constexpr float u_c = 0.23f, u_m = 1.0f, u_csi = 0.8f, u_so = 0.3f;
+    constexpr float r_sn = 1.2f, k_ = 3.0f, b_so = 0.84f, c_so = 0.02f;
+    constexpr float c_so_half = (float)(0.5 * (0.115 - 0.009));   // 0.5*(a_so - tau_a), fenton.py:83
+    constexpr float r_diff = (float)(0.02 - 1.2);                 // (r_sp - r_sn),      fenton.py:89
+    const float dt = a.p.dt;
+    float V = s[0], W = s[1], S = s[2];
+
+    // H(x) = (1+sign x)/2, G(x) = (1-sign x)/2 (fenton.py:73-79): 0.5 at x == 0
+    const float Hc = U > u_c ? 1.f : (U < u_c ? 0.f : 0.5f);
+    const float Hso = U > u_so ? 1.f : (U < u_so ? 0.f : 0.5f);
+    const float Gso = 1.f - Hso;
+
+    const float I_fi = (-V * Hc) * (U - u_c) * (u_m - U) * (1.0f / tau_d);
+    const float I_si = (-W * S) * (1.0f / tau_si);
+    const float I_so = c_so_half * (1.f + tanhf((U - b_so) * (1.0f / c_so))) +
+                       (U * Gso) * (1.0f / tau_so) + Hso * tau_a;
+    const float dU = -(I_fi + I_si + I_so);
+    const float dV = U > u_c ? -V * (1.0f / tau_vp) : (1.f - V) * (1.0f / tau_vn);
+    // tau_wn1 == tau_wn2 == 75 (fenton.py:53-54): the inner tf.where is an identity
+    const float dW = U > u_c ? -W * (1.0f / tau_wp) : (1.f - W) * (1.0f / tau_wn);
+    const float r_s = fmaf(r_diff, Hc, r_sn);
+    const float dS = r_s * (0.5f * (1.f + tanhf((U - u_csi) * k_)) - S);
+
+    Unew = fmaf(a.p.ddt, lap, fmaf(dt, dU, U0));
+    s[0] = fmaf(dt, dV, V);
+    s[1] = fmaf(dt, dW, W);
+    s[2] = fmaf(dt, dS, S);
+  }
+};
+
+}  // namespace fib

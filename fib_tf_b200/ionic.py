@@ -1,0 +1,320 @@
+"""
+fib_tf_b200.ionic -- host-side mirror of the reference's IonicModel base class (ionic.py:30-307).
+
+Same public surface (config dict -> attributes, add_hole_to_phase_field, define,
+add_pace_op / fire_op, the run() generator, millisecond_to_step, image, pot, ode_op,
+jit_scope / context-manager fallback), so the reference's driver loops
+
+    model = Fenton4v(config); model.add_hole_to_phase_field(256, 256, 30); model.define()
+    model.add_pace_op('s2', 'luq', 1.0)
+    for i in model.run(im):
+        if i == s2: model.fire_op('s2')
+
+run unchanged -- but every device operation goes to libfibb200.so (hand-written sm_100a CUDA
+kernels behind the C ABI in include/fib_b200.h) instead of a TensorFlow session.  NumPy is used
+for set-up only (initial conditions, phase field, Chebyshev fit), exactly where the reference
+uses it.  There is no TensorFlow, no XLA and no CPU fallback.
+
+Extra, optional config keys (all default to the reference's behaviour):
+    device       CUDA device ordinal (default: LOCAL_RANK when distributed, else 0)
+    graph        replay one CUDA graph per run() iteration (default True)
+    distributed  row-shard the grid over the torch.distributed world (default False)
+    lut          Courtemanche: V-only intermediates from the 150x30 table (default False)
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _capi
+from .sharding import partition_rows
+
+
+class DeviceVar:
+    """Stand-in for a tf.Variable holding one state plane: .eval() reads it back
+    (fenton.py:152-153, court.py:619), .assign(a) uploads, var[r, c].eval() probes one cell."""
+
+    def __init__(self, model, name):
+        self._model = model
+        self.name = name
+
+    def eval(self):
+        return self._model._gather(self._model._ctx.get_state(self.name))
+
+    def local(self):
+        return self._model._ctx.get_state(self.name)
+
+    def assign(self, value):
+        m = self._model
+        a = np.broadcast_to(np.asarray(value, dtype=np.float32), (m.height, m.width))
+        m._ctx.set_state(self.name, a[m._row0:m._row0 + m._rows])
+        return self
+
+    def __getitem__(self, idx):
+        return _Cell(self, int(idx[0]), int(idx[1]))
+
+
+class _Cell:
+    def __init__(self, var, row, col):
+        self.var, self.row, self.col = var, row, col
+
+    def eval(self):
+        return self.var._model._probe(self.var.name, self.row, self.col)
+
+
+class IonicModel:
+    """Base class for cardiac electrophysiology simulation (mirror of ionic.py:30)."""
+
+    MODEL_ID = None         # set by subclasses
+
+    def __init__(self, config):
+        for key, val in config.items():     # ionic.py:35-37
+            setattr(self, key, val)
+        self.phase = None
+        self._ops = {}
+        self.defined = False
+        self.dt_per_step = 1
+        self.cl_observer = None
+        self._ctx = None
+        self._rank, self._nranks = 0, 1
+        if config.get('distributed'):
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("config['distributed'] needs torch.distributed.init_process_group first")
+            self._rank, self._nranks = dist.get_rank(), dist.get_world_size()
+        parts = partition_rows(self.height, self._nranks)
+        self._row0, self._rows = parts[self._rank]
+        # host copy of the phase field covers these global rows (everything when not sharded)
+        self._phase_row0 = max(self._row0 - 1, 0)
+        self._phase_row1 = min(self._row0 + self._rows + 1, self.height)
+
+    # ---- the reference's graph-building helpers have no meaning without TensorFlow ----------
+    def _no_graph(self, name):
+        raise NotImplementedError(
+            'IonicModel.%s built TensorFlow graph nodes in the reference (ionic.py); in fib_tf_b200 '
+            'the stencil and the ionic update are fused CUDA kernels selected by the model class. '
+            'Custom TensorFlow-expressed models are out of scope.' % name)
+
+    def laplace(self, X0):
+        self._no_graph('laplace')
+
+    def phase_field(self, X):
+        self._no_graph('phase_field')
+
+    def enforce_boundary(self, X):
+        self._no_graph('enforce_boundary')
+
+    def rush_larsen(self, g, g_inf, g_tau, dt, name=None):
+        self._no_graph('rush_larsen')
+
+    # ---- geometry (ionic.py:83-105) ----------------------------------------------------------
+    def add_hole_to_phase_field(self, x, y, radius, neg=False):
+        """Adds a circular hole centred at (x, y) = (column, row) to the phase field; with
+        neg=True the inside is kept and the outside excluded.  Must precede define()."""
+        if self.defined:
+            raise AssertionError('add_hole_to_phase_field should be called before calling define')
+        r0, r1 = self._phase_row0, self._phase_row1
+        if self.phase is None:
+            self.phase = np.ones([r1 - r0, self.width], dtype=np.float32)
+        xx, yy = np.meshgrid(np.arange(self.width), np.arange(r0, r1))
+        dist = np.hypot(xx - x, yy - y)
+        if neg:
+            self.phase *= np.array(0.5 * (np.tanh(0.1 * (radius - dist)) + 1.0), dtype=np.float32)
+        else:
+            self.phase *= np.array(0.5 * (np.tanh(dist - radius) + 1.0), dtype=np.float32)
+        # floor at 1e-5 to avoid division by 0 in the phase-field term (ionic.py:104-105)
+        self.phase = np.maximum(self.phase, 1e-5)
+
+    # ---- device context ---------------------------------------------------------------------
+    def _make_context(self, flags=0):
+        cfgd = self.__dict__
+        device = cfgd.get('device')
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0)) if self._nranks > 1 else 0
+        if not cfgd.get('graph', True):
+            flags |= _capi.F_NO_GRAPH
+        sharded = self._nranks > 1
+        ctx = _capi.Context(self.MODEL_ID, self.height, self.width, self.dt, self.diff, flags=flags,
+                            device=device, row0=self._row0 if sharded else 0,
+                            rows=self._rows if sharded else 0)
+        if self.phase is not None:
+            ctx.set_phase(np.asarray(self.phase, dtype=np.float32), self._phase_row0)
+        if sharded:
+            import torch.distributed as dist
+            box = [_capi.comm_unique_id() if self._rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(self._nranks, self._rank, box[0])
+        self._ctx = ctx
+        return ctx
+
+    def _local_full(self, value):
+        """[rows, W] fp32 array filled with `value` for this shard's rows."""
+        return np.full([self._rows, self.width], value, dtype=np.float32)
+
+    def _gather(self, local):
+        if self._nranks == 1:
+            return local
+        import torch.distributed as dist
+        parts = [None] * self._nranks
+        dist.all_gather_object(parts, local)
+        return np.concatenate(parts, axis=0)
+
+    def _probe(self, name, row, col):
+        """One cell of a state plane; in a sharded run the owner rank reads it and shares it."""
+        own = self._row0 <= row < self._row0 + self._rows
+        v = self._ctx.probe(name, row, col) if own else None
+        if self._nranks == 1:
+            return v
+        import torch.distributed as dist
+        vals = [None] * self._nranks
+        dist.all_gather_object(vals, v)
+        return [x for x in vals if x is not None][0]
+
+    # ---- stimulation (ionic.py:125-169) ------------------------------------------------------
+    def add_pace_op(self, name, loc, v):
+        """Registers a stimulator: pot := max(pot, s), s = v inside the named region and min_v
+        elsewhere.  loc in left/right/top/bottom/luq/llq/ruq/rlq.  Must follow define()."""
+        if not self.defined:
+            raise AssertionError('add_hole_to_phase_field should be called after calling define')
+        H, W = self.height, self.width
+        regions = {
+            'left': (0, H, 0, 5), 'right': (0, H, W - 5, W), 'top': (0, 5, 0, W),
+            'bottom': (H - 5, H, 0, W), 'luq': (1, H // 2, 1, W // 2),
+            'llq': (H // 2, H - 1, 1, W // 2), 'ruq': (1, H // 2, W // 2, W - 1),
+            'rlq': (H // 2, H - 1, W // 2, W - 1),
+        }
+        rect = regions.get(loc)
+        if rect is None:
+            print('undefined pace location')      # ionic.py:161-162: the op still clamps at min_v
+            rect = (0, 0, 0, 0)
+        self._ops[name] = ('pace', rect, float(v))
+
+    def fire_op(self, name):
+        """Executes an op registered by add_pace_op (or a model op such as 'slow')."""
+        op = self._ops[name]
+        if op[0] == 'pace':
+            (r0, r1, c0, c1), v = op[1], op[2]
+            self._ctx.stimulate(self._pot_name, max(r0, 0), r1, max(c0, 0), c1, v, float(self.min_v))
+        elif op[0] == 'call':
+            op[1]()
+
+    # ---- the run() generator (ionic.py:171-245) ----------------------------------------------
+    def run(self, im=None, keep_state=False, block=True):
+        """Generator: advances the model one iteration (= dt_per_step time steps) per yield.
+
+            for i in model.run(im):
+                if i == s2: model.fire_op('s2')
+        """
+        if not self.defined:
+            raise AssertionError('define() must be called before run()')
+        then = time.time()
+        v0 = self.min_v
+        last_spike = 0
+        self.samples = int(self.duration / (self.dt_per_step * self.dt))
+        plot_every = max(int(self.dt_per_plot / self.dt_per_step), 1)
+        watch = bool(im) or self.cl_observer is not None
+        prow, pcol = 20, self.width // 2                         # ionic.py:216
+        for i in range(self.samples):
+            self._ctx.step(self.ode_op(i), 1)
+            yield i
+            if watch and i % plot_every == 0:
+                if im:
+                    image = self.image()
+                    if self.phase is not None:
+                        image *= self.phase
+                    im.imshow(image)
+                    v1 = image[prow, pcol]
+                elif prow < self.height:
+                    v1 = self._probe_image(prow, pcol)
+                else:
+                    continue
+                if v1 >= 0.5 and v0 < 0.5:
+                    cl = (i - last_spike) * self.dt_per_step * self.dt
+                    if self.cl_observer is None:
+                        print('wavefront reaches the middle top point at %d, cycle length is %d' % (i, cl))
+                    else:
+                        self.cl_observer(i, cl)
+                    last_spike = i
+                v0 = v1
+        if keep_state:                                           # ionic.py:226-229
+            self.state = {}
+            for s in self._State:
+                self.state[s] = self._State[s].eval()
+        if getattr(self, 'timeline', False):
+            self._write_timeline()
+        self._ctx.sync()
+        print('elapsed: %f sec' % (time.time() - then))
+        if block and im:
+            im.wait()
+
+    def _probe_image(self, row, col):
+        v = float(self._probe(self._pot_name, row, col))
+        v = self._normalise(v)
+        if self.phase is not None and self._phase_row0 <= row < self._phase_row1:
+            v *= float(self.phase[row - self._phase_row0, col])
+        return v
+
+    def _normalise(self, v):
+        return (v - self.min_v) / (self.max_v - self.min_v)
+
+    def _write_timeline(self):
+        """The reference traces ONE extra iteration after the loop with TF's FULL_TRACE
+        (ionic.py:231-241), which also advances the state once more.  Here: CUDA-event timing of
+        one extra iteration, written as a chrome-trace JSON to config['timeline_name']."""
+        c = self._ctx
+        c.sync()
+        n0 = c.launch_count()
+        c.timer_start()
+        c.step(self.ode_op(self.samples), 1)
+        c.timer_stop()
+        ms = c.timer_ms()
+        ev = [{'name': 'ode_op (%d fused step kernels)' % (c.launch_count() - n0), 'ph': 'X',
+               'pid': 0, 'tid': 0, 'ts': 0, 'dur': ms * 1000.0,
+               'args': {'cells': self.height * self.width, 'dt_per_step': self.dt_per_step}}]
+        with open(self.timeline_name, 'w') as f:
+            json.dump({'traceEvents': ev}, f)
+
+    def millisecond_to_step(self, t):
+        """Converts t in milliseconds to the iteration count returned by run()."""
+        return int(t / (self.dt_per_step * self.dt))
+
+    def define(self, s1=True):
+        """Placeholder replaced in subclasses: builds the initial state and the device context."""
+        self.defined = True
+
+    def image(self):
+        """[height x width] float ndarray in 0..1 encoding the transmembrane potential."""
+        pass
+
+    def pot(self):
+        """Handle of the transmembrane variable."""
+        pass
+
+    def ode_op(self, tick):
+        """The op run once per iteration (ionic.py:277-286)."""
+        if hasattr(self, '_ode_op'):
+            return self._ode_op
+        elif tick % self.fast_slow_ratio == 0:
+            return self._ode_slow_op
+        else:
+            return self._ode_fast_op
+
+    # ---- dummy context, as when XLA is unavailable (ionic.py:288-307) ------------------------
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def jit_scope(self):
+        return self
+
+    # ---- extras ---------------------------------------------------------------------------------
+    def sync(self):
+        self._ctx.sync()
+
+    def close(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None

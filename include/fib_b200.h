@@ -1,0 +1,174 @@
+/*
+ * fib_b200.h -- C ABI of libfibb200.so: a B200-native (sm_100a) explicit time-stepper for
+ * 2-D cardiac monodomain models (Fenton 4v, Beeler-Reuter, Courtemanche).
+ *
+ * The reference (siravan/fib_tf) has NO native boundary: its hot path is a TensorFlow-1.x
+ * graph executed once per run() iteration by tf.Session.run (ionic.py:202-204).  This header
+ * is the boundary a maintainer binds instead of TensorFlow; every entry point names the
+ * reference interface (file:line under /root/reference) whose device work it replaces.
+ * The Python side (fib_tf_b200/_capi.py) binds exactly these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative fib_status on error; the message
+ *     is available from fib_last_error() (thread-local, valid until the next failing call);
+ *   - host pointers are borrowed for the duration of the call only; planes are row-major
+ *     [rows][width] fp32 with no padding on the host side;
+ *   - all device work is ENQUEUE-ONLY on the context's stream unless stated "synchronous"
+ *     (the reference's run() generator hands control back to user code between iterations,
+ *     ionic.py:202-204, so the only sync points are state reads, probes and fib_sync);
+ *   - one context is not thread-safe (single caller); different contexts are independent;
+ *   - there is no CPU fallback: without a CUDA device fib_create fails with FIB_E_CUDA.
+ */
+#ifndef FIB_B200_H_
+#define FIB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIB_ABI_VERSION 1
+
+typedef struct fib_ctx fib_ctx;
+
+typedef enum {
+  FIB_OK = 0,
+  FIB_E_ARG = -1,     /* bad argument / bad ordering of calls              */
+  FIB_E_CUDA = -2,    /* CUDA runtime error (message holds the CUDA string) */
+  FIB_E_NCCL = -3,    /* NCCL error or libnccl not loadable                 */
+  FIB_E_STATE = -4    /* context not in a state that allows the call        */
+} fib_status;
+
+/* model ids -- the reference's model classes */
+typedef enum {
+  FIB_FENTON4V = 0,     /* fenton.py:31   Fenton4v,  4 state planes U V W S            */
+  FIB_BR = 1,           /* br.py:30       BeelerReuter, 8 planes V C M H J D F XI     */
+  FIB_COURT = 2,        /* court.py:30    Courtemanche, 21 planes, fast/slow split    */
+  FIB_COURT_ULTRA = 3   /* court_ultra.py:32  all states every step (+ optional _us_) */
+} fib_model;
+
+/* flag bits of fib_config.flags */
+#define FIB_F_CHEBY      0x01u  /* BR: degree-8 polynomial gates   (br.py:207-252, config 'cheby') */
+#define FIB_F_SKIP       0x02u  /* BR: multi-rate slow gates        (br.py:96-107,  config 'skip')  */
+#define FIB_F_LUT        0x04u  /* Courtemanche: V-only intermediates from the 150x30 table,
+                                   truncating lookup i=int(V+100) clamped (courtemanche.h:354-357) */
+#define FIB_F_ULTRA_SLOW 0x08u  /* court_ultra.py:81-82,198-199,221-222: 22nd state '_us_'         */
+#define FIB_F_NO_CHRONIC 0x10u  /* Courtemanche: chronic-AF remodelling OFF (court.py:41 sets it ON) */
+#define FIB_F_NO_GRAPH   0x20u  /* launch kernels directly instead of replaying a CUDA graph         */
+
+typedef struct {
+  uint32_t struct_size;      /* = sizeof(fib_config), for ABI evolution                              */
+  int32_t  model;            /* fib_model                                                            */
+  int32_t  height, width;    /* GLOBAL grid, config 'height'/'width' (ionic.py:35-37); both >= 3     */
+  double   dt;               /* config 'dt'   (ms); kept double: the reference folds diff*dt and dt*n
+                                in Python doubles before rounding to fp32 (fenton.py:103, br.py:197) */
+  double   diff;             /* config 'diff'                                                        */
+  uint32_t flags;            /* FIB_F_*                                                              */
+  int32_t  device;           /* CUDA device ordinal                                                  */
+  int32_t  row0, rows;       /* this shard = global rows [row0, row0+rows); rows == 0 -> whole grid   */
+  int32_t  steps_per_launch; /* temporal blocking: time steps fused per kernel launch (0/1 = off);
+                                must divide dt_per_step                           */
+  int32_t  reserved[6];
+} fib_config;
+
+/* ops of fib_step -- the reference's session ops */
+typedef enum {
+  FIB_OP_ODE = 0,   /* model._ode_op: one run() iteration = dt_per_step time steps
+                       (fenton.py:135-145: 10, br.py:96-120: 5, court.py:91-102: 1)                  */
+  FIB_OP_SLOW = 1   /* model._ops['slow'] (court.py:103): the 17 slow states, step 10*dt, evaluated
+                       on the CURRENT state; a no-op for every other model (court_ultra.py:108)      */
+} fib_op;
+
+/* table ids of fib_set_table / fib_get_table */
+typedef enum {
+  FIB_TABLE_BR_CHEBY = 0,   /* float[12][9]: rows 2g = inf, 2g+1 = tau of gate g in (xi,m,h,j,d,f);
+                               coefficients d_i of the scaled monomials S_i (br.py:303-331)          */
+  FIB_TABLE_COURT_LUT = 1   /* float[150][30]: courtemanche.h:105-134 column order, row i = V i-100 mV */
+} fib_table;
+
+/* ---- library ----------------------------------------------------------------------- */
+int         fib_version(void);            /* FIB_ABI_VERSION of the loaded library                   */
+const char *fib_last_error(void);
+int         fib_device_count(int *count); /* cudaGetDeviceCount; FIB_E_CUDA if no driver/device       */
+
+/* ---- life cycle: replaces tf.Session()/tf.Variable creation in define() ---------------
+ * (fenton.py:126-131, br.py:85-94, court.py:85-89) */
+int fib_create(const fib_config *cfg, fib_ctx **out);
+int fib_destroy(fib_ctx *ctx);
+
+/* ---- model description ----------------------------------------------------------------- */
+int         fib_num_vars(const fib_ctx *ctx);               /* 4 / 8 / 21 / 21|22                   */
+const char *fib_var_name(const fib_ctx *ctx, int var);      /* reference names: "U","V",..,"_Na_i_"  */
+int         fib_var_index(const fib_ctx *ctx, const char *name);   /* <0 if unknown                 */
+int         fib_dt_per_step(const fib_ctx *ctx);            /* model.dt_per_step                     */
+
+/* ---- state I/O: replaces tf.Variable(initial) and Variable.eval() ----------------------
+ * (fenton.py:128-131,152-153; br.py:86-93,341; court.py:89; ionic.py:226-229).
+ * `n` must equal rows*width of THIS shard.  Synchronous. */
+int fib_set_state(fib_ctx *ctx, int var, const float *host, size_t n);
+int fib_get_state(fib_ctx *ctx, int var, float *host, size_t n);
+/* sub-rectangle read of the local shard (frame grabs / strided probes); global coordinates */
+int fib_get_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float *host);
+
+/* ---- phase field: replaces self.phi = tf.Variable(self.phase) (ionic.py:55-58) ---------
+ * `rows_host` holds global rows [first_row, first_row+nrows) of the [H][W] phase field and must
+ * cover this shard plus one row either side (clipped to the grid).  NULL removes the field. */
+int fib_set_phase(fib_ctx *ctx, const float *rows_host, int first_row, int nrows);
+
+/* ---- tables ------------------------------------------------------------------------------ */
+int fib_set_table(fib_ctx *ctx, int table, const float *data, size_t n);
+int fib_get_table(fib_ctx *ctx, int table, float *data, size_t n);
+/* Courtemanche: fill the LUT on the device by evaluating the kernel's own calc_inter at
+ * V = i-100 mV, i = 0..149 (courtemanche.h:473-479 init_table). */
+int fib_build_lut(fib_ctx *ctx);
+/* Courtemanche calc_inter(V) (court.py:273-429 / courtemanche.h:159-285) for n voltages:
+ * out[n][32]; columns 0..29 in courtemanche.h:105-134 order, 30 = us_infinity, 31 = tau_us
+ * (court_ultra.py:445-450).  Synchronous.  Backs Courtemanche.calc_inter(V, np) / _Inter. */
+int fib_court_inter(fib_ctx *ctx, const float *v_host, size_t n, float *out_host);
+
+/* ---- the hot path: replaces sess.run(self.ode_op(i)) (ionic.py:203) and
+ * fire_op('slow') (ionic.py:165-169, court.py:103).  Enqueues n_iter iterations. */
+int fib_step(fib_ctx *ctx, int op, int n_iter);
+/* lock-step stepping of several shards living in ONE process (row-adjacent, ctxs[0] on top):
+ * halo rows are exchanged device-to-device after every time step.  Used to emulate the
+ * multi-GPU decomposition on one device and for single-process multi-GPU. */
+int fib_step_group(fib_ctx **ctxs, int n, int op, int n_iter);
+
+/* ---- stimulus: replaces pot().assign(tf.maximum(pot(), s)) (ionic.py:144-163) -----------
+ * X := max(X, inside [r0,r1)x[c0,c1) ? value : floor_v) over the whole plane, GLOBAL coords. */
+int fib_stimulate(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float value,
+                  float floor_v);
+
+/* ---- probes: replaces Variable[r,c] reads (ionic.py:216, court.py:109-110) --------------
+ * Synchronous.  FIB_E_ARG if (row,col) is not in this shard. */
+int fib_probe(fib_ctx *ctx, int var, int row, int col, float *out);
+/* weighted mean of a plane over this shard: sum(w*x), sum(w) (w = phase field, or 1 if none):
+ * backs np.average(x, weights=phase) in court_ultra.py:466-480.  Synchronous. */
+int fib_weighted_sum(fib_ctx *ctx, int var, double *sum_wx, double *sum_w);
+
+/* ---- sync / timing / accounting ------------------------------------------------------------ */
+int fib_sync(fib_ctx *ctx);
+int fib_timer_start(fib_ctx *ctx);            /* cudaEventRecord on the context's stream        */
+int fib_timer_stop(fib_ctx *ctx);
+int fib_timer_ms(fib_ctx *ctx, float *ms);    /* synchronises on the stop event                 */
+int fib_launch_count(const fib_ctx *ctx, uint64_t *kernels);  /* kernels launched so far        */
+int fib_stream(const fib_ctx *ctx, void **cuda_stream);       /* the cudaStream_t, for interop   */
+
+/* ---- pinned host memory for the host<->device legs ---------------------------------------- */
+int fib_host_alloc(size_t bytes, void **out);
+int fib_host_free(void *p);
+
+/* ---- multi-process row sharding: one process per GPU, halo rows over NCCL ----------------
+ * fib_comm_unique_id writes a 128-byte ncclUniqueId (rank 0 calls it; the bytes are
+ * broadcast by the host side, e.g. torch.distributed).  After fib_comm_init, fib_step
+ * exchanges one halo row of the diffusing variable with rank-1 / rank+1 after every time
+ * step (ncclSend/ncclRecv on a side stream, overlapped with the interior rows). */
+int fib_comm_unique_id(void *out128);
+int fib_comm_init(fib_ctx *ctx, int nranks, int rank, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIB_B200_H_ */

@@ -25,6 +25,9 @@ Fixture layout (np.savez_compressed):
     s{i}__{var}     [H,W] fp32 state plane `var` after the loop body of iteration i
     probe           [samples] fp32  pot()[probe_row, probe_col] after each iteration
     trend           [n,2] fp32   (court.py only)
+    meta['noise']   {'s{i}__{var}': e}: rel_err (oracle/monodomain_np.py) between two runs of the
+                    unmodified reference that differ ONLY in the fp32 math library used for
+                    exp/expm1/log/tanh/pow (NumPy's vs correctly rounded) -- the noise floor.
 """
 import json
 import os
@@ -83,7 +86,9 @@ def state_of(model, kind):
 
 
 def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=None,
-             s1=True, trend_op=False):
+             s1=True, trend_op=False, _alt=False):
+    from oracle.monodomain_np import rel_err, var_scale
+    shim.ALT_LIBM = _alt
     shim.reset_registry()
     model = MODELS[kind](cfg)
     for h in holes:
@@ -114,12 +119,24 @@ def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=
     finally:
         sys.stdout.close()
         sys.stdout = sys.__stdout__
+        shim.ALT_LIBM = False
+    if _alt:
+        return out
+    noise = {}
+    if probe is None:
+        # second pass of the unmodified reference with the alternate fp32 libm: its deviation from
+        # the first pass is the reference's own noise floor (see tfshim.ALT_LIBM)
+        alt = run_case(name, kind, cfg, holes, paces, slow_every, snaps, probe, s1, trend_op,
+                       _alt=True)
+        for k in out:
+            if k.startswith('s') and '__' in k:
+                noise[k] = rel_err(alt[k], out[k], var_scale(kind, k.split('__', 1)[1]))
     meta = {
         'name': name, 'model': kind, 'config': cfg, 'holes': [list(h) for h in holes],
         'paces': [list(p) for p in paces], 'slow_every': slow_every,
         'snaps': sorted(snaps), 'probe': list(probe) if probe else None,
         'dt_per_step': model.dt_per_step, 'samples': model.samples, 's1': bool(s1),
-        'vars': sorted(state_of(model, kind).keys()),
+        'vars': sorted(state_of(model, kind).keys()), 'noise': noise,
         'generator': 'oracle/make_golden.py (unmodified reference under oracle/tfshim.py)',
         'numpy': np.__version__,
     }

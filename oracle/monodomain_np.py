@@ -495,6 +495,39 @@ def court_solve(S, dt, diff, phase=None, multirate=True, chronic=True, ultra_slo
 
 
 # --------------------------------------------------------------------------
+# the parity metric
+# --------------------------------------------------------------------------
+def var_scale(kind, name):
+    """Dynamic range of a state variable: the scale of the absolute floor of the metric."""
+    if kind == 'fenton4v':
+        return 1.0
+    if kind == 'br':
+        return {'V': 120.0, 'C': 1e-5}.get(name, 1.0)
+    return {'V': 150.0, '_Na_i_': 11.17, '_K_i_': 139.0, '_Ca_i_': 1e-3, '_Ca_rel_': 1.488,
+            '_Ca_up_': 1.488}.get(name, 1.0)
+
+
+def rel_err(got, ref, scale):
+    """max |got-ref| / max(|ref|, 1e-3*scale): per-cell relative error with a floor at 0.1 % of
+    the variable's dynamic range (the metric of SURVEY.md Appendix B.2)."""
+    den = np.maximum(np.abs(ref), 1e-3 * scale)
+    with np.errstate(invalid='ignore'):
+        return float(np.nanmax(np.abs(np.asarray(got, np.float64) - ref) / den))
+
+
+PARITY_RTOL = 1e-5      # north_star: 1e-5 relative per step over the first 100 steps
+NOISE_FACTOR = 3.0      # ... but never tighter than 3x the reference's own fp32 libm noise
+
+
+def parity_tolerance(meta, key):
+    """Tolerance (in the rel_err metric) for snapshot plane `key` = 's{i}__{var}' of a fixture:
+    max(1e-5, 3 * noise), where noise is the deviation of the UNMODIFIED reference from itself
+    when its exp/expm1/log/tanh/pow are evaluated by another correctly-rounding fp32 libm
+    (oracle/tfshim.ALT_LIBM; recorded in the fixture by oracle/make_golden.py)."""
+    return max(PARITY_RTOL, NOISE_FACTOR * meta.get('noise', {}).get(key, 0.0))
+
+
+# --------------------------------------------------------------------------
 # a small driver with the reference's iteration structure
 # --------------------------------------------------------------------------
 class OracleModel:

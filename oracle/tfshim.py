@@ -181,11 +181,28 @@ def constant(v, dtype=None, name=None):
     return Node(lambda: a, [])
 
 
+# ALT_LIBM: evaluate the transcendental functions in float64 and round once to float32, i.e. run
+# the reference with a DIFFERENT but equally legitimate (in fact correctly rounded) fp32 math
+# library.  |reference(ALT_LIBM) - reference(NumPy fp32 libm)| is the reference's own sensitivity
+# to <= 1-ulp differences in exp/expm1/log/tanh/pow -- the noise floor below which "parity" with
+# any other fp32 implementation (TF/Eigen, XLA, CUDA) has no meaning (see oracle/make_golden.py).
+ALT_LIBM = False
+_TRANSCENDENTAL = {np.exp, np.expm1, np.log, np.tanh}
+
+
+def _apply(uf, a):
+    a = _coerce(a)
+    if ALT_LIBM and uf in _TRANSCENDENTAL:
+        with np.errstate(all='ignore'):
+            return uf(np.asarray(a, dtype=np.float64)).astype(F32)
+    return uf(a)
+
+
 def _unary(uf):
     def f(x, name=None):
         if isinstance(x, Node):
-            return Node(lambda a: uf(_coerce(a)), [x])
-        return Node(lambda: uf(_coerce(x)), [])
+            return Node(lambda a: _apply(uf, a), [x])
+        return Node(lambda: _apply(uf, x), [])
     return f
 
 
@@ -200,8 +217,15 @@ reciprocal = _unary(np.reciprocal)
 abs = _unary(np.abs)            # noqa: A001  (mirrors tf.abs)
 
 
+def _pow(a, b):
+    a, b = _coerce(a), _coerce(b)
+    if ALT_LIBM:
+        return np.power(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)).astype(F32)
+    return np.power(a, b)
+
+
 def pow(x, y, name=None):       # noqa: A001
-    return Node(lambda a, b: np.power(_coerce(a), _coerce(b)), [x, y])
+    return Node(_pow, [x, y])
 
 
 def maximum(x, y, name=None):

@@ -1,0 +1,239 @@
+"""GPU: the CUDA path (through the C ABI, via the drop-in Python API) against
+  (1) the golden fixtures = the UNMODIFIED reference executed under oracle/tfshim.py,
+  (2) the NumPy oracle run live on the same seeded inputs at 512^2,
+  (3) size-independent properties at the full benchmark sizes.
+
+Tolerance (written here, used everywhere below): for every state variable and snapshot,
+    rel_err = max |cuda - ref| / max(|ref|, 1e-3 * range(var))  <=  max(1e-5, 3 * noise)
+where `noise` is the reference's own deviation from itself when ONLY its fp32 math library is
+swapped for another correctly-rounding one (recorded per plane in the fixture, see
+oracle/make_golden.py / oracle/tfshim.ALT_LIBM).  1e-5 is BASELINE.json's per-step bar; the noise
+term exists because near the removable singularities of the BR / Courtemanche rate functions the
+reference's fp32 result is itself only defined to ~1e-4 (it is never looser than 3x that)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_fixture
+from oracle import monodomain_np as onp
+
+pytestmark = pytest.mark.gpu
+
+SHORT = [n for n in golden_names() if 'long' not in n]
+LONG = [n for n in golden_names() if 'long' in n]
+
+
+@pytest.fixture(scope='module')
+def cuda(cuda_device):
+    import cuda_adapter
+    return cuda_adapter
+
+
+@pytest.mark.parametrize('name', SHORT)
+def test_per_step_parity_with_reference_fixture(cuda, name):
+    meta, arr = load_fixture(name)
+    seen = []
+
+    def check(i, m):
+        for v in meta['vars']:
+            key = 's%d__%s' % (i, v)
+            e = onp.rel_err(m.state[v], arr[key], onp.var_scale(meta['model'], v))
+            tol = onp.parity_tolerance(meta, key)
+            assert e <= tol, '%s %s: rel_err %.3e > tol %.3e' % (name, key, e, tol)
+        seen.append(i)
+
+    m, _ = onp.run_fixture(meta, check, model_factory=cuda.CudaModel)
+    m.close()
+    assert seen == meta['snaps']
+
+
+def crossings(trace, level, dt_iter):
+    """Linear-interpolated times (ms) at which the trace crosses `level` upwards / downwards."""
+    t = np.asarray(trace, dtype=np.float64)
+    up, dn = [], []
+    for i in range(1, len(t)):
+        if t[i - 1] < level <= t[i]:
+            up.append((i - 1 + (level - t[i - 1]) / (t[i] - t[i - 1])) * dt_iter)
+        if t[i - 1] >= level > t[i]:
+            dn.append((i - 1 + (t[i - 1] - level) / (t[i - 1] - t[i])) * dt_iter)
+    return up, dn
+
+
+@pytest.mark.parametrize('name', LONG)
+def test_long_horizon_apd_and_activation_time(cuda, name):
+    """One full action potential on a strip: activation time at the probe (conduction velocity)
+    and action-potential duration must match the reference within 1 % (BASELINE.json)."""
+    meta, arr = load_fixture(name)
+    m, trace = onp.run_fixture(meta, None, model_factory=cuda.CudaModel)
+    m.close()
+    lo, hi = onp.OracleModel.RANGE[meta['model']]
+    level = lo + 0.3 * (hi - lo) if meta['model'] != 'fenton4v' else 0.3
+    dt_iter = meta['dt_per_step'] * meta['config']['dt']
+    up_r, dn_r = crossings(arr['probe'], level, dt_iter)
+    up_c, dn_c = crossings(trace, level, dt_iter)
+    assert len(up_r) >= 1 and len(dn_r) >= 1 and len(up_c) == len(up_r) and len(dn_c) == len(dn_r)
+    assert abs(up_c[0] - up_r[0]) <= 0.01 * up_r[0]                     # activation time -> CV
+    apd_r, apd_c = dn_r[0] - up_r[0], dn_c[0] - up_c[0]
+    assert abs(apd_c - apd_r) <= 0.01 * apd_r, (apd_c, apd_r)
+    # and the whole trace stays close in absolute terms (1 % of the voltage range)
+    assert np.max(np.abs(trace - arr['probe'])) <= 0.01 * (hi - lo)
+
+
+def model_noise(kind):
+    worst = 0.0
+    for n in SHORT:
+        meta, _ = load_fixture(n)
+        if meta['model'] == kind:
+            worst = max([worst] + list(meta['noise'].values()))
+    return worst
+
+
+@pytest.mark.parametrize('kind,cfg,iters', [
+    ('fenton4v', dict(diff=1.5), 10),
+    ('br', dict(diff=0.809, cheby=True, skip=False), 20),
+    ('br', dict(diff=0.809, cheby=False, skip=True), 20),
+    ('court', dict(diff=0.809, width=256, height=256), 100),
+    ('court_ultra', dict(diff=1.5, width=256, height=256, ultra_slow=True), 100),
+])
+def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
+    """BASELINE configs 1-2 (512^2 with the shipped holes) and Courtemanche at 256^2: 100 time
+    steps, every state variable, against the oracle run here on the same inputs."""
+    base = {'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'duration': 10,
+            'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False,
+            'cheby': False, 'ultra_slow': False}
+    base.update(cfg)
+    W = base['width']
+    ref, gpu = onp.OracleModel(kind, base), cuda.CudaModel(kind, base)
+    for m in (ref, gpu):
+        m.add_hole(W // 2, W // 2, 30 * W // 512)
+        m.define()
+        m.add_pace('s2', 'luq', 1.0 if kind == 'fenton4v' else 10.0)
+    tol = max(1e-5, 3 * model_noise(kind))
+    for i in range(iters):
+        for m in (ref, gpu):
+            m.iterate()
+            if kind == 'court' and i % 10 == 0:
+                m.fire('slow')
+            if i == iters // 2:
+                m.fire('s2')
+    for v in ref.state:
+        e = onp.rel_err(gpu.state[v], ref.state[v], onp.var_scale(kind, v))
+        assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (kind, v, e, tol)
+    gpu.close()
+
+
+@pytest.mark.parametrize('kind,extra', [('fenton4v', {}), ('br', {'cheby': True, 'skip': True}),
+                                        ('court', {}), ('court_ultra', {'ultra_slow': True})])
+def test_row_shards_are_bit_identical_to_the_unsharded_run(cuda, kind, extra):
+    """Emulates R row shards in one process (fib_step_group, device-to-device halo rows) and
+    requires BIT-IDENTICAL planes: sharding must not change arithmetic; seams are interior."""
+    from fib_tf_b200 import _capi
+    from fib_tf_b200.sharding import partition_rows
+    cfg = {'width': 72, 'height': 45, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.1, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False,
+           'cheby': False, 'ultra_slow': False}
+    cfg.update(extra)
+    whole = cuda.CudaModel(kind, cfg)
+    whole.add_hole(30, 20, 7)
+    whole.define()
+    m = whole.m
+    c0 = m._ctx
+    flags = m._flags() if hasattr(m, '_flags') else (
+        (_capi.F_CHEBY if cfg['cheby'] else 0) | (_capi.F_SKIP if cfg['skip'] else 0)
+        if kind == 'br' else 0)
+    parts = partition_rows(cfg['height'], 4)
+    shards = [_capi.Context(m.MODEL_ID, cfg['height'], cfg['width'], cfg['dt'], cfg['diff'],
+                            flags=flags | _capi.F_NO_GRAPH, row0=r0, rows=n) for r0, n in parts]
+    for s, (r0, n) in zip(shards, parts):
+        for v in c0.var_names:
+            s.set_state(v, c0.get_state(v)[r0:r0 + n])
+        s.set_phase(m.phase, 0)
+        if kind == 'br':
+            s.set_table(_capi.TABLE_BR_CHEBY, m.chebyshev_table())
+    for it in range(6):
+        c0.step(_capi.OP_ODE, 1)
+        _capi.step_group(shards, _capi.OP_ODE, 1)
+        if kind == 'court' and it % 2 == 0:
+            c0.step(_capi.OP_SLOW, 1)
+            _capi.step_group(shards, _capi.OP_SLOW, 1)
+        if it == 2:     # a stimulus crossing the seams
+            args = (c0.var_names[0], 5, 40, 3, 30, float(m.max_v) * 0.5, float(m.min_v))
+            c0.stimulate(*args)
+            for s in shards:
+                s.stimulate(*args)
+    for v in c0.var_names:
+        full = c0.get_state(v)
+        got = np.concatenate([s.get_state(v) for s in shards], axis=0)
+        assert np.array_equal(full, got), 'variable %s differs between sharded and unsharded' % v
+    for s in shards:
+        s.close()
+    whole.close()
+
+
+def test_cuda_graph_replay_is_bit_identical_to_direct_launches(cuda):
+    cfg = {'width': 100, 'height': 64, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.809, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': True,
+           'cheby': True, 'ultra_slow': False}
+    a, b = cuda.CudaModel('br', cfg), cuda.CudaModel('br', cfg, graph=False)
+    for m in (a, b):
+        m.add_hole(40, 30, 8)
+        m.define()
+        for _ in range(7):
+            m.iterate()
+    for v in a.m._ctx.var_names:
+        assert np.array_equal(a.state[v], b.state[v]), v
+    a.close()
+    b.close()
+
+
+def test_planar_wave_property_at_4096(cuda):
+    """Size-independent property at the benchmark size: with the y-uniform S1 initial state every
+    row of a 4096-wide grid evolves identically, and equals the oracle's 5-row strip of the same
+    width within the parity tolerance."""
+    cfg = {'width': 4096, 'height': 4096, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False}
+    gpu = cuda.CudaModel('fenton4v', cfg)
+    gpu.define()
+    ref = onp.OracleModel('fenton4v', dict(cfg, height=5))
+    ref.define()
+    for _ in range(5):
+        gpu.iterate()
+        ref.iterate()
+    for v in ('U', 'V', 'W', 'S'):
+        a = gpu.state[v]
+        assert np.array_equal(a, np.broadcast_to(a[0], a.shape)), 'rows differ for %s' % v
+        assert onp.rel_err(a[:5], ref.state[v], 1.0) <= 1e-5
+    gpu.close()
+
+
+def test_uniform_rest_state_stays_uniform_at_4096(cuda):
+    """A uniform field has a Laplacian of exactly 0 in fp32 (4c + 2c - 6c), so a uniform BR state
+    must stay exactly uniform at any size."""
+    cfg = {'width': 4096, 'height': 4096, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.809,
+           'duration': 1, 'timeline': False, 'timeline_name': 'x', 'save_graph': False,
+           'skip': False, 'cheby': True}
+    gpu = cuda.CudaModel('br', cfg)
+    gpu.define(False)
+    for _ in range(4):
+        gpu.iterate()
+    for v in gpu.m._ctx.var_names:
+        a = gpu.state[v]
+        assert a.min() == a.max(), v
+    gpu.close()
+
+
+def test_empty_and_edge_geometries(cuda):
+    """Smallest legal grid (3x3), a width that is not a multiple of the vector width, a stimulus
+    with an empty rectangle, and an n_iter of 0."""
+    for H, W in ((3, 3), (3, 7), (9, 5), (17, 33)):
+        cfg = {'width': W, 'height': H, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.0, 'duration': 1,
+               'timeline': False, 'timeline_name': 'x', 'save_graph': False}
+        ref, gpu = onp.OracleModel('fenton4v', cfg), cuda.CudaModel('fenton4v', cfg)
+        for m in (ref, gpu):
+            m.define()
+            m.iterate()
+        gpu.m._ctx.step(0, 0)
+        gpu.m._ctx.stimulate('U', 0, 0, 0, 0, 1.0, 0.0)
+        ref.state['U'] = np.maximum(ref.state['U'], np.float32(0.0))
+        for v in ('U', 'V', 'W', 'S'):
+            assert onp.rel_err(gpu.state[v], ref.state[v], 1.0) <= 1e-5, (H, W, v)
+        gpu.close()
