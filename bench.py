@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""
+bench.py -- BASELINE.json's headline measurement: Gcell-steps/s (and % of the HBM roofline) of the
+Fenton 4v spiral-wave fibrillation run on a 32768x32768 grid, row-sharded over N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one run() iteration of the reference driver loop = dt_per_step = 10 explicit time
+steps of the whole grid (fenton.py:133-138).  STRONG scaling: the 32768^2 grid is fixed, each rank
+owns 32768/N rows.  Rank 0 prints exactly ONE JSON line on stdout.
+
+  value     device-timed (CUDA events on the library's stream, max over ranks), state resident in
+            HBM; the state (16 GiB) is >> the 126 MB L2, so no flush is needed between steps.
+  e2e       the same K iterations through the public drop-in API (Fenton4v.run() generator) with
+            HOST buffers inside the timed region: strip-wise upload of the full initial state
+            from pinned memory (H2D), the headless cycle-length probe every iteration (D2H) and a
+            full-frame grab into pinned memory every 10th iteration (the cadence of fenton.py:184).
+  roofline  HBM-bound: 32 B per cell-step (4 fp32 planes read + written once) x cells per launch
+            / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference
+            the oracle's plain-C + OpenMP port of the same step (oracle/csrc/monodomain_cpu.c) on
+            all host cores, on a bounded 2048^2 mirror-tiled sample of the same workload.
+            (TensorFlow, the reference's real CPU path, is not installable in this image.)
+"""
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 512
+B_ALG = 32.0        # bytes per cell-step: 4 state planes x (read + write) x 4 B  
+METRIC = 'Gcell-steps/s'
+FALLBACK_HBM = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def fenton_config(size, duration, distributed=False, **kw):
+    cfg = {'width': size, 'height': size, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5,
+           'duration': duration, 'timeline': False, 'timeline_name': 'unused.json',
+           'save_graph': False, 'distributed': distributed}
+    cfg.update(kw)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic input: a developed 512^2 spiral, mirror-tiled
+# ---------------------------------------------------------------------------------------------
+def spiral_tile_gpu(device):
+    """S1-S2 protocol of fenton.py:155-185 on 512^2 (no hole) run to 400 ms on the GPU."""
+    from fib_tf_b200.fenton import Fenton4v
+    m = Fenton4v(fenton_config(TILE, 400, device=device))
+    m.define()
+    m.add_pace_op('s2', 'luq', 1.0)
+    s2 = m.millisecond_to_step(210)
+    m._ctx.step(0, s2 + 1)
+    m.fire_op('s2')
+    m._ctx.step(0, m.millisecond_to_step(400) - s2 - 1)
+    tile = {n: m._State[n].local() for n in ('U', 'V', 'W', 'S')}
+    m.close()
+    return tile
+
+
+def strips_of(tile_plane, width):
+    """[512, width] strips for even / odd tile rows: alternate tiles are mirrored so that every
+    tile seam is a mirror plane, i.e. a no-flux boundary of the small problem."""
+    pair = np.hstack([tile_plane, tile_plane[:, ::-1]])
+    reps = -(-width // pair.shape[1])
+    even = np.tile(pair, reps)[:, :width]
+    return even, even[::-1]
+
+
+def upload_tiled(ctx, tile, row0, rows, width, pinned):
+    """Strip-wise H2D upload of the mirror-tiled state for global rows [row0, row0+rows)."""
+    nbytes = 0
+    for name, plane in tile.items():
+        even, odd = strips_of(plane, width)
+        pinned[0][:] = even
+        pinned[1][:] = odd
+        g = row0
+        while g < row0 + rows:
+            t, r = divmod(g, TILE)
+            n = min(TILE - r, row0 + rows - g)
+            ctx.set_rect(name, g, 0, pinned[t & 1][r:r + n])
+            nbytes += n * width * 4
+            g += n
+    return nbytes
+
+
+def tiled_host(tile, size):
+    out = {}
+    for name, plane in tile.items():
+        even, odd = strips_of(plane, size)
+        blocks = [(even if (t & 1) == 0 else odd) for t in range(-(-size // TILE))]
+        out[name] = np.ascontiguousarray(np.vstack(blocks)[:size])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) >= 8 and f[0] == str(self.device):
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), r[4:8]):
+                if v.lower() == 'active':
+                    reasons.add(name)
+        smax = [float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit()]
+        pw = [float(r[3]) for r in self.rows if r[3].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(self.rows),
+                'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's C/OpenMP port on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_run(tile, iterations, budget_s, sample=2048):
+    """Times `iterations` run() iterations (10 steps each) of the C port on a sample^2
+    mirror-tiled grid; stops early when the time budget is spent.  -> (gcell_steps_per_s, info)"""
+    from oracle import cpu_port
+    L = cpu_port.port()
+    st = tiled_host(tile, sample)
+    tmp = np.empty_like(st['U'])
+
+    u, t = st['U'], tmp
+    per_iter = []
+    t_all = time.perf_counter()
+    done = 0
+    for it in range(iterations + 1):            # first iteration is the warm-up
+        t0 = time.perf_counter()
+        for _ in range(10):
+            L.fib_cpu_fenton_step(sample, sample, u, t, st['V'], st['W'], st['S'], None, 0.1, 1.5)
+            u, t = t, u
+        dt = time.perf_counter() - t0
+        if it > 0:
+            per_iter.append(dt)
+            done += 1
+        if time.perf_counter() - t_all > budget_s and done >= 1:
+            break
+    sec = float(np.mean(per_iter))
+    val = sample * sample * 10 / sec / 1e9
+    info = {'value': val, 'unit': METRIC, 'cores': int(L.fib_cpu_threads()), 'kind': 'port',
+            'sample': 'oracle C/OpenMP port, Fenton 4v %dx%d mirror-tiled spiral, %d iterations x 10 '
+                      'steps (%.2f s/iteration); reference publishes 0.052 Gcell-steps/s for its TF '
+                      'CPU path on a 1.7 GHz quad-core (details.md:264)' % (sample, sample, done, sec),
+            'host_cpus': os.cpu_count()}
+    return val, sec, done, info
+
+
+def cpu_tile():
+    """The spiral tile for the CPU legs: from the GPU when there is one, else a committed-free
+    analytic stand-in (throughput is value-independent to first order)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return spiral_tile_gpu(0)
+    except Exception as e:      # noqa: BLE001
+        log('cpu_tile: GPU spiral unavailable (%s); using the S1 initial state' % e)
+    from oracle import monodomain_np as onp
+    return onp.fenton_init(TILE, TILE)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    tile = cpu_tile()
+    val, sec, done, info = cpu_sample_run(tile, args.steps, budget_s=150.0)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': METRIC, 'n_gpus': args.gpus,
+        'steps': done, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.size, args.gpus),
+        'cpu_baseline': info,
+        'e2e': {'value': val, 'unit': METRIC, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'note': 'reference arm = the reference algorithm on host cores (oracle C/OpenMP port; '
+                'TensorFlow is not installable offline); each step is one run() iteration of a '
+                'bounded 2048^2 sample of the workload',
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(size, n):
+    return {'workload': 'Fenton 4v spiral-wave fibrillation %dx%d (BASELINE.json configs[4]), dt=0.1 ms, '
+                        'diff=1.5, no phase field, mirror-tiled developed 512^2 spiral' % (size, size),
+            'grid': [size, size], 'time_steps_per_step': 10, 'parallelism': 'row-shard x%d' % n,
+            'halo': '1 row of U per neighbour per time step over NCCL send/recv' if n > 1 else 'none',
+            'l2': 'state %.1f GiB >> 126 MB L2: no flush needed' % (size * size * 16 / 2 ** 30),
+            'seed': 0}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--size', type=int, default=32768)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from fib_tf_b200 import _capi
+    from fib_tf_b200.fenton import Fenton4v
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: fib_tf_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    K, Wm, size = args.steps, max(args.warmup, 3), args.size
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    tile = spiral_tile_gpu(local)
+    model = Fenton4v(fenton_config(size, K * 10 * 0.1, distributed=world > 1, device=local))
+    model.define(s1=False)
+    ctx = model._ctx
+    row0, rows = model._row0, model._rows
+    pinned = [_capi.pinned_empty((TILE, size)), _capi.pinned_empty((TILE, size))]
+    upload_tiled(ctx, tile, row0, rows, size, pinned)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.step(0, Wm)                                     # warm-up (also instantiates the graph)
+    barrier()
+    n0 = ctx.launch_count()
+    ctx.timer_start()
+    ctx.step(0, K)
+    ctx.timer_stop()
+    ms_dev = ctx.timer_ms()
+    barrier()
+    launches_rank = ctx.launch_count() - n0
+    ms = max_over_ranks(ms_dev)
+    launches = int(sum_over_ranks(launches_rank))
+    cells = float(size) * size
+    value = cells * K * 10 / (ms * 1e-3) / 1e9
+
+    # ---- e2e through the public API, host buffers inside the timed region ----
+    frame = _capi.pinned_empty((rows, size))
+    probes = []
+    model.cl_observer = lambda i, cl: probes.append((i, cl))
+    d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    h2d = upload_tiled(ctx, tile, row0, rows, size, pinned)
+    with contextlib.redirect_stdout(sys.stderr):
+        for i in model.run(None):
+            if i % 10 == 0:                               # frame grab cadence of fenton.py:184
+                ctx.get_state('U', out=frame)
+                d2h += frame.nbytes
+    d2h += 4 * K                                          # the per-iteration probe read
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = cells * K * 10 / e2e_s / 1e9
+    clocks = sampler.stop()
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'of measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = FALLBACK_HBM, 'of fallback (B200_PROFILING.md)'
+    launch_ms = ms_dev / max(launches_rank, 1)
+    achieved = B_ALG * rows * size / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get('fenton4v_step')
+        if tj:
+            traffic = tj['dram_bytes_per_cell'] * rows * size
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'kernel': 'fib::step_kernel<Fenton4v,...>', 'bytes_per_cell_step': B_ALG,
+                'avg_launch_ms': launch_ms, 'cells_per_launch': rows * size}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(size, world),
+        'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': sum_over_ranks(h2d) / K,
+                'd2h_bytes_per_step': sum_over_ranks(d2h) / K, 'seconds': e2e_s},
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        _v, _s, _d, info = cpu_sample_run(tile, 8, budget_s=20.0)
+        line['cpu_baseline'] = info
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for p in pinned + [frame]:
+        _capi.pinned_free(p)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfibb200.so')
+# FIB_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get('FIB_B200_LIB') or os.path.join(_HERE, 'libfibb200.so')
 
 # model ids / flags / ops / tables: keep in sync with include/fib_b200.h
 FENTON4V, BR, COURT, COURT_ULTRA = 0, 1, 2, 3
@@ -57,6 +58,7 @@ _SIGNATURES = {
     'fib_set_state': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_state': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_rect': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'fib_set_rect': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     'fib_set_phase': (C.c_int, [_P, _P, C.c_int, C.c_int]),
     'fib_set_table': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_table': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
@@ -188,6 +190,10 @@ class Context:
         out = np.empty((r1 - r0, c1 - c0), dtype=np.float32)
         check(lib().fib_get_rect(self._h, self.var(var), r0, r1, c0, c1, out.ctypes.data_as(_P)))
         return out
+
+    def set_rect(self, var, r0, c0, block):
+        a, p = _f32c(block)
+        check(lib().fib_set_rect(self._h, self.var(var), r0, r0 + a.shape[0], c0, c0 + a.shape[1], p))
 
     def set_phase(self, phase_rows, first_row=0):
         if phase_rows is None:

@@ -113,7 +113,8 @@ struct fib_ctx {
   int cur = 0;
   float* s[S_COUNT] = {nullptr};      // other planes
   float* phase = nullptr;             // halo layout
-  float* lut = nullptr;               // 150 x 30
+  float* lut = nullptr;               // 150 x 30, the ABI layout (courtemanche.h order)
+  float* lut_t = nullptr;             // 30 x 160 transposed copy the kernels read
   bool have_lut = false, have_cheb = false, halo_dirty = true, comm_pending = false;
   float cheb[12][9];
   uint64_t launches = 0;
@@ -176,6 +177,12 @@ __global__ void court_inter_kernel(const float* __restrict__ v, int n, float* __
   for (int k = 0; k < ncols; ++k) out[(size_t)i * ncols + k] = q[k];
 }
 
+__global__ void lut_transpose_kernel(const float* __restrict__ lut, float* __restrict__ lut_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLutRows) return;
+  for (int k = 0; k < kLutCols; ++k) lut_t[k * kLutTStride + i] = lut[i * kLutCols + k];
+}
+
 __global__ void court_lut_kernel(float* __restrict__ lut) {   // courtemanche.h:473-479
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kLutRows) return;
@@ -224,6 +231,10 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   if (row0 < 0 || rows < 1 || row0 + rows > cfg->height)
     return fail(FIB_E_ARG, "shard rows [%d,%d) outside the grid of height %d", row0, row0 + rows,
                 cfg->height);
+  if ((long long)(rows + 2) * ((cfg->width + 31) / 32 * 32) >= (1LL << 31))
+    return fail(FIB_E_ARG, "shard of %d rows x %d columns exceeds 2^31 cells per plane: the kernels "
+                "index planes with 32-bit element offsets; shard the grid over more GPUs", rows,
+                cfg->width);
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev)
@@ -265,7 +276,11 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
     CU(cudaMemsetAsync(c->s[k], 0, c->plane_floats() * sizeof(float), c->stream));
   }
   CU(cudaMalloc(&c->red, 2 * sizeof(double)));
-  if (cfg->model >= FIB_COURT) CU(cudaMalloc(&c->lut, sizeof(float) * kLutRows * kLutCols));
+  if (cfg->model >= FIB_COURT) {
+    CU(cudaMalloc(&c->lut, sizeof(float) * kLutRows * kLutCols));
+    CU(cudaMalloc(&c->lut_t, sizeof(float) * kLutCols * kLutTStride));
+    CU(cudaMemsetAsync(c->lut_t, 0, sizeof(float) * kLutCols * kLutTStride, c->stream));
+  }
   memset(c->cheb, 0, sizeof c->cheb);
   CU(cudaStreamSynchronize(c->stream));
   *out = c;
@@ -283,6 +298,7 @@ extern "C" int fib_destroy(fib_ctx* c) {
   for (int k = 0; k < S_COUNT; ++k) cudaFree(c->s[k]);
   cudaFree(c->phase);
   cudaFree(c->lut);
+  cudaFree(c->lut_t);
   cudaFree(c->red);
   cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev_stop);
@@ -350,6 +366,20 @@ extern "C" int fib_get_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1,
   return 0;
 }
 
+extern "C" int fib_set_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host) {
+  if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
+    return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
+  DevGuard dg(c->cfg.device);
+  float* dst = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch + c0;
+  CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)(c1 - c0) * sizeof(float),
+                       (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (var == 0) c->halo_dirty = true;
+  return 0;
+}
+
 extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
@@ -395,7 +425,10 @@ extern "C" int fib_set_table(fib_ctx* c, int table, const float* data, size_t n)
     if (n != (size_t)kLutRows * kLutCols)
       return fail(FIB_E_ARG, "Courtemanche LUT must hold 150*30 floats, got %zu", n);
     CU(cudaMemcpyAsync(c->lut, data, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    lut_transpose_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut, c->lut_t);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    c->launches++;
     c->have_lut = true;
     return 0;
   }
@@ -426,7 +459,9 @@ extern "C" int fib_build_lut(fib_ctx* c) {
   DevGuard dg(c->cfg.device);
   court_lut_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut);
   CU(cudaGetLastError());
-  c->launches++;
+  lut_transpose_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut, c->lut_t);
+  CU(cudaGetLastError());
+  c->launches += 2;
   c->have_lut = true;
   return 0;
 }
@@ -463,7 +498,7 @@ static void fill_common(fib_ctx* c, StepArgs<M>& a, int lr0, int nrows) {
   a.xout = c->x[c->cur ^ 1];
   for (int k = 0; k < M::NS; ++k) a.s[k] = c->s[k];
   a.phase = c->phase;
-  a.lut = c->lut;
+  a.lut = c->lut_t;
   a.lr0 = lr0;
   a.nrows = nrows;
 }
@@ -518,7 +553,9 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
         a.p.neg_dt = (float)(-dt);
         a.p.neg_dt_slow = (float)(-(dt * n));
         a.p.ddt = (float)(c->cfg.diff * dt);
-        memcpy(a.p.cheb, c->cheb, sizeof c->cheb);
+        // S_i = 2^(i-1) x^i (br.py:289-301): hand the kernel plain monomial coefficients
+        for (int g = 0; g < 12; ++g)
+          for (int i = 0; i < 9; ++i) a.p.poly[g][i] = i < 2 ? c->cheb[g][i] : ldexpf(c->cheb[g][i], i - 1);
         return launch_step<M>(c->g, a, c->stream, c->sms);
       };
       if (cheby) e = n > 0 ? go(BeelerReuter<true, true>()) : go(BeelerReuter<true, false>());

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fib_math.cuh"
+
 namespace fib {
 
 // Geometry of one shard.  Planes are SoA fp32, row pitch `pitch` floats (multiple of 32 -> every
@@ -48,7 +50,12 @@ __device__ __forceinline__ float clip_nan(float x, float lo, float hi) {
 // IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).
 // neg_dt = fp32(-dt) (or fp32(-(dt*n)) folded in double on the host, br.py:197-200).
 __device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, float neg_dt) {
-  float e = expm1f(neg_dt / tau);
+  float e = m_expm1(m_div(neg_dt, tau));
+  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+}
+// gates whose dt/tau is small except in rare cells (everything but the fast sodium activation)
+__device__ __forceinline__ float rush_larsen_slow(float g, float g_inf, float tau, float neg_dt) {
+  float e = m_expm1_small(m_div(neg_dt, tau));
   return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 // same with e = expm1(-dt/tau) precomputed (Python-scalar tau: court.py:189,243)

@@ -11,6 +11,8 @@
 //   * only the diffusing variable is ping-ponged (xin -> xout); every other plane is updated in
 //     place, so the algorithmic traffic is exactly one read + one write per state variable.
 #pragma once
+#include <stdlib.h>
+
 #include "fib_stencil.cuh"
 
 namespace fib {
@@ -20,6 +22,7 @@ namespace fib {
 //   NEED_RAW      reaction term reads the un-enforced centre value (Fenton 4v, fenton.py:101)
 //   NEED_LAP      step needs the stencil (false for the Courtemanche 'slow' op)
 //   STORE_X       step writes the diffusing variable
+//   MIN_BLOCKS    resident CTAs per SM the register allocator must leave room for
 //   stores(k)     plane k is written by this step
 //   struct Params (uniform scalars / small tables; lives in the kernel parameter bank)
 //   cell(p, xraw, x0, lap, s[NS], xnew)
@@ -29,7 +32,7 @@ struct StepArgs {
   float* xout;                   // ping-pong target (halo layout)
   float* s[M::NS > 0 ? M::NS : 1];  // non-diffusing planes (in place)
   const float* phase;            // halo layout, or nullptr
-  const float* lut;              // Courtemanche 150x30 table (global), or nullptr
+  const float* lut;              // Courtemanche table, transposed [30][160] (global), or nullptr
   int lr0, nrows;                // local row range [lr0, lr0+nrows) processed by this launch
   typename M::Params p;
 };
@@ -37,7 +40,7 @@ struct StepArgs {
 constexpr int kBX = 32;   // threads along columns (one warp)
 
 template <class M, int VEC, int R, int BY, bool PHASE>
-__global__ void __launch_bounds__(kBX* BY)
+__global__ void __launch_bounds__(kBX* BY, M::MIN_BLOCKS)
 step_kernel(const Geom g, const StepArgs<M> a) {
   M::prologue(a);   // e.g. stage the Courtemanche LUT in shared memory
   const int c = (blockIdx.x * kBX + threadIdx.x) * VEC;
@@ -46,43 +49,42 @@ step_kernel(const Geom g, const StepArgs<M> a) {
   const int gend = min(gr0 + R, g.row0 + a.lr0 + a.nrows);    // one past my last row
   if (c >= g.W || gr0 >= gend) return;
 
-  const size_t pitch = g.pitch;
-  const bool col_edge = !(c >= 2 && c + VEC <= g.W - 2);
+  // All plane offsets are 32-bit ELEMENT indices (one IMAD.WIDE per address); fib_create rejects
+  // shards with (rows+2)*pitch >= 2^31.
+  const int pitch = g.pitch;
+  const ColWindow<VEC> cw(c, g.W);
+  // element index of the start of (clamped / reflected) global row `gr` in a halo-layout plane
+  auto xrow = [&](int gr) { return (clampi(gr, 1, g.H - 2) - g.row0 + 1) * pitch; };
+  auto prow = [&](int gr) { return (reflecti(gr, g.H) - g.row0 + 1) * pitch; };
 
   float xN[VEC + 2], xC[VEC + 2], xS[VEC + 2];
   float pN[VEC + 2], pC[VEC + 2], pS[VEC + 2];   // phase-field window (REFLECT padding)
   if (M::NEED_LAP) {
-    load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr0 - 1, 1, g.H - 2) - g.row0 + 1) * pitch, c,
-                           g.W, xN);
+    load_enforced_row<VEC>(a.xin, xrow(gr0 - 1), cw, g.W, xN);
     if (PHASE) {
-      load_reflect_row<VEC>(a.phase + (size_t)(reflecti(gr0 - 1, g.H) - g.row0 + 1) * pitch, c,
-                            g.W, pN);
-      load_reflect_row<VEC>(a.phase + (size_t)(gr0 - g.row0 + 1) * pitch, c, g.W, pC);
+      load_reflect_row<VEC>(a.phase, prow(gr0 - 1), cw, g.W, pN);
+      load_reflect_row<VEC>(a.phase, prow(gr0), cw, g.W, pC);
     }
   }
-  load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr0, 1, g.H - 2) - g.row0 + 1) * pitch, c, g.W,
-                         xC);
+  load_enforced_row<VEC>(a.xin, xrow(gr0), cw, g.W, xC);
 
+  int off = (gr0 - g.row0) * pitch + c;          // my cell in a non-halo plane; += pitch per row
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
+  for (int i = 0; i < R; ++i, off += pitch) {
     const int gr = gr0 + i;
     if (gr < gend) {
       if (M::NEED_LAP) {
-        load_enforced_row<VEC>(a.xin + (size_t)(clampi(gr + 1, 1, g.H - 2) - g.row0 + 1) * pitch,
-                               c, g.W, xS);
-        if (PHASE)
-          load_reflect_row<VEC>(a.phase + (size_t)(reflecti(gr + 1, g.H) - g.row0 + 1) * pitch, c,
-                                g.W, pS);
+        load_enforced_row<VEC>(a.xin, xrow(gr + 1), cw, g.W, xS);
+        if (PHASE) load_reflect_row<VEC>(a.phase, prow(gr + 1), cw, g.W, pS);
       }
       // raw centre values: differ from the enforced ones only on the global border ring
       float xraw[VEC];
-      if (M::NEED_RAW && (col_edge || gr == 0 || gr == g.H - 1)) {
-        VecIO<VEC>::ld(a.xin + (size_t)(gr - g.row0 + 1) * pitch + c, xraw);
+      if (M::NEED_RAW && (!cw.interior_x || gr == 0 || gr == g.H - 1)) {
+        VecIO<VEC>::ld(a.xin + (off + pitch), xraw);
       } else {
 #pragma unroll
         for (int l = 0; l < VEC; ++l) xraw[l] = xC[l + 1];
       }
-      const size_t off = (size_t)(gr - g.row0) * pitch + c;
       float sv[M::NS > 0 ? M::NS : 1][VEC];
 #pragma unroll
       for (int k = 0; k < M::NS; ++k) VecIO<VEC>::ld(a.s[k] + off, sv[k]);
@@ -108,7 +110,7 @@ step_kernel(const Geom g, const StepArgs<M> a) {
 #pragma unroll
       for (int k = 0; k < M::NS; ++k)
         if (M::stores(k)) VecIO<VEC>::st(a.s[k] + off, sv[k]);
-      if (M::STORE_X) VecIO<VEC>::st(a.xout + (size_t)(gr - g.row0 + 1) * pitch + c, xnew);
+      if (M::STORE_X) VecIO<VEC>::st(a.xout + (off + pitch), xnew);
 
       if (M::NEED_LAP) {
 #pragma unroll
@@ -118,8 +120,7 @@ step_kernel(const Geom g, const StepArgs<M> a) {
           for (int j = 0; j < VEC + 2; ++j) { pN[j] = pC[j]; pC[j] = pS[j]; }
         }
       } else if (i + 1 < R && gr + 1 < gend) {
-        load_enforced_row<VEC>(
-            a.xin + (size_t)(clampi(gr + 1, 1, g.H - 2) - g.row0 + 1) * pitch, c, g.W, xC);
+        load_enforced_row<VEC>(a.xin, xrow(gr + 1), cw, g.W, xC);
       }
     }
   }
@@ -142,6 +143,11 @@ inline cudaError_t launch_step_p(const Geom& g, const StepArgs<M>& a, cudaStream
   const long bx = (ncg + kBX - 1) / kBX;
   auto blocks = [&](int R) { return bx * (((a.nrows + R - 1) / R + BY - 1) / BY); };
   const long want = 4L * sms;
+  static const int force = getenv("FIB_FORCE_R") ? atoi(getenv("FIB_FORCE_R")) : 0;   // experiments
+  if (force == 8 && M::MAX_R >= 8) return launch_step_r<M, VEC, (M::MAX_R >= 8 ? 8 : 1), BY, PHASE>(g, a, st);
+  if (force == 4 && M::MAX_R >= 4) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
+  if (force == 2 && M::MAX_R >= 2) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);
+  if (force == 1) return launch_step_r<M, VEC, 1, BY, PHASE>(g, a, st);
   if (M::MAX_R >= 8 && blocks(8) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 8 ? 8 : 1), BY, PHASE>(g, a, st);
   if (M::MAX_R >= 4 && blocks(4) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
   if (M::MAX_R >= 2 && blocks(2) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);

@@ -1,0 +1,102 @@
+// fib_math.cuh -- the transcendental / division layer of the ionic kernels.
+//
+// BR and Courtemanche are instruction-issue bound, not HBM bound: with
+// CUDA's IEEE division (~10 instr + slow path) and libm-grade expf/expm1f/logf/tanhf (12-35
+// instr) the BR cell costs ~700 instructions.  This layer replaces them by few-ulp versions built
+// on the SFU approximations (MUFU.EX2 / LG2 / RCP), each <= ~3 ulp -- the same error class as
+// swapping one fp32 libm for another, which is exactly what the parity tolerance is calibrated
+// against (oracle/tfshim.ALT_LIBM, tests/test_gpu_parity.py).
+// Build with -DFIB_ACCURATE_MATH=1 to get IEEE division and CUDA's libm instead (A/B checks).
+#pragma once
+#include <cuda_runtime.h>
+
+#ifndef FIB_ACCURATE_MATH
+#define FIB_ACCURATE_MATH 0
+#endif
+
+namespace fib {
+
+__device__ __forceinline__ float sfu_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+#if FIB_ACCURATE_MATH
+__device__ __forceinline__ float m_rcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ float m_div(float a, float b) { return a / b; }
+__device__ __forceinline__ float m_exp(float x) { return expf(x); }
+__device__ __forceinline__ float m_expm1(float x) { return expm1f(x); }
+__device__ __forceinline__ float m_expm1_small(float x) { return expm1f(x); }
+__device__ __forceinline__ float m_log(float x) { return logf(x); }
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+// 1 / (1 + e^{-2z}) == 0.5 (1 + tanh z)
+__device__ __forceinline__ float m_half_1p_tanh(float z) { return 0.5f * (1.f + tanhf(z)); }
+#else
+__device__ __forceinline__ float m_rcp(float x) { return sfu_rcp(x); }                 // 1 ulp
+__device__ __forceinline__ float m_div(float a, float b) { return a * sfu_rcp(b); }    // 2 ulp
+
+// e^x = 2^t * 2^r, t = fl(x*log2e), r = the rounding error of that product + x*lo(log2e),
+// 2^r ~ 1 + r ln2.  ~2 ulp over the whole range; +inf / 0 on overflow / underflow like expf.
+__device__ __forceinline__ float m_exp(float x) {
+  const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.92596299112661746e-8f;
+  const float t = x * L2E_HI;
+  float r = fmaf(x, L2E_HI, -t);
+  r = fmaf(x, L2E_LO, r);
+  return sfu_ex2(t) * fmaf(r, 0.693147182464599609375f, 1.0f);
+}
+
+// expm1: degree-7 Taylor polynomial for |x| < 0.25 (truncation x^7/8! < 1e-8 relative), exp(x)-1
+// beyond (|result| >= 0.22 there, so the subtraction costs < 5 ulp).  Both sides are computed and
+// selected, so there is no divergence.
+__device__ __forceinline__ float m_expm1(float x) {
+  float p = 1.98412698412698e-4f;                 // 1/7!
+  p = fmaf(p, x, 1.38888888888889e-3f);           // 1/6!
+  p = fmaf(p, x, 8.33333333333333e-3f);           // 1/5!
+  p = fmaf(p, x, 4.16666666666667e-2f);           // 1/4!
+  p = fmaf(p, x, 1.66666666666667e-1f);           // 1/3!
+  p = fmaf(p, x, 0.5f);
+  p = fmaf(p * x, x, x);                          // x + x^2 (1/2 + x/3! + ...)
+  const float e = m_exp(x) - 1.0f;
+  return fabsf(x) < 0.25f ? p : e;
+}
+
+// Same function for arguments that are USUALLY small (|x| = dt/tau of every gate except the fast
+// sodium activation): the exp() side is only evaluated when some lane of the warp needs it
+// (warp-uniform branch, no divergence), which removes ~8 instructions per gate on the common path.
+__device__ __forceinline__ float m_expm1_small(float x) {
+  float p = 1.98412698412698e-4f;
+  p = fmaf(p, x, 1.38888888888889e-3f);
+  p = fmaf(p, x, 8.33333333333333e-3f);
+  p = fmaf(p, x, 4.16666666666667e-2f);
+  p = fmaf(p, x, 1.66666666666667e-1f);
+  p = fmaf(p, x, 0.5f);
+  p = fmaf(p * x, x, x);
+  const bool big = !(fabsf(x) < 0.25f);
+  if (__any_sync(__activemask(), big)) p = big ? m_exp(x) - 1.0f : p;
+  return p;
+}
+
+__device__ __forceinline__ float m_log(float x) { return sfu_lg2(x) * 0.693147182464599609375f; }
+__device__ __forceinline__ float m_sqrt(float x) { return sfu_sqrt(x); }
+__device__ __forceinline__ float m_half_1p_tanh(float z) {
+  return sfu_rcp(1.0f + m_exp(-2.0f * z));
+}
+#endif
+
+}  // namespace fib

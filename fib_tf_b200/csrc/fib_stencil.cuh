@@ -16,31 +16,48 @@ namespace fib {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int reflecti(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
 
-// e[j] = Xp[row][c-1+j], j = 0..VEC+1, from the row pointer of the (already row-clamped) raw row.
+// Column indices of the VEC+2 window entries of a thread owning columns [c, c+VEC): row-invariant,
+// computed once per thread.  `interior` threads (the overwhelming majority) read one aligned vector
+// plus the two neighbours; edge threads gather through the clamped / reflected indices.
 template <int VEC>
-__device__ __forceinline__ void load_enforced_row(const float* __restrict__ rowp, int c, int W,
+struct ColWindow {
+  int c;                 // first owned column
+  bool interior_x;       // c-1 >= 1 && c+VEC <= W-2  (no clamping needed for the diffusing variable)
+  bool interior_p;       // c-1 >= 0 && c+VEC <= W-1  (no reflection needed for the phase field)
+  __device__ __forceinline__ ColWindow(int c_, int W)
+      : c(c_), interior_x(c_ >= 2 && c_ + VEC <= W - 2), interior_p(c_ >= 1 && c_ + VEC <= W - 1) {}
+};
+
+// e[j] = Xp[row][c-1+j], j = 0..VEC+1; `row` = element index of the row start (32-bit: the host
+// guarantees (rows+2)*pitch < 2^31), already row-clamped by the caller.
+template <int VEC>
+__device__ __forceinline__ void load_enforced_row(const float* __restrict__ x, int row,
+                                                  const ColWindow<VEC>& cw, int W,
                                                   float (&e)[VEC + 2]) {
-  if (c >= 2 && c + VEC <= W - 2) {          // fully interior group: one vector load + 2 edges
-    VecIO<VEC>::ld(rowp + c, &e[1]);
-    e[0] = rowp[c - 1];
-    e[VEC + 1] = rowp[c + VEC];
+  if (cw.interior_x) {
+    const float* p = x + (row + cw.c);
+    VecIO<VEC>::ld(p, &e[1]);
+    e[0] = p[-1];
+    e[VEC + 1] = p[VEC];
   } else {
 #pragma unroll
-    for (int j = 0; j < VEC + 2; ++j) e[j] = rowp[clampi(c - 1 + j, 1, W - 2)];
+    for (int j = 0; j < VEC + 2; ++j) e[j] = x[row + clampi(cw.c - 1 + j, 1, W - 2)];
   }
 }
 
 // p[j] = phi_pad[row][c-1+j] with REFLECT columns.
 template <int VEC>
-__device__ __forceinline__ void load_reflect_row(const float* __restrict__ rowp, int c, int W,
+__device__ __forceinline__ void load_reflect_row(const float* __restrict__ ph, int row,
+                                                 const ColWindow<VEC>& cw, int W,
                                                  float (&p)[VEC + 2]) {
-  if (c >= 1 && c + VEC <= W - 1) {
-    VecIO<VEC>::ld(rowp + c, &p[1]);
-    p[0] = rowp[c - 1];
-    p[VEC + 1] = rowp[c + VEC];
+  if (cw.interior_p) {
+    const float* q = ph + (row + cw.c);
+    VecIO<VEC>::ld(q, &p[1]);
+    p[0] = q[-1];
+    p[VEC + 1] = q[VEC];
   } else {
 #pragma unroll
-    for (int j = 0; j < VEC + 2; ++j) p[j] = rowp[clampi(reflecti(c - 1 + j, W), 0, W - 1)];
+    for (int j = 0; j < VEC + 2; ++j) p[j] = ph[row + clampi(reflecti(cw.c - 1 + j, W), 0, W - 1)];
   }
 }
 

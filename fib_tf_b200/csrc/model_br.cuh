@@ -1,8 +1,33 @@
 // model_br.cuh -- modified 8-variable Beeler-Reuter model, pointwise part.
 // Restates br.py:125-173 (solve), :175-205 (exact gates), :207-252 (Chebyshev gates),
 // :255-273 (alpha/beta), :289-331 (scaled-monomial expansion), coefficients br.py:49-62.
+//
+// Instruction budget (this kernel is issue-bound, not HBM-bound): see fib_math.cuh.  Beyond the
+// few-ulp transcendental layer two algebraic identities are used, both exact in real arithmetic:
+//   * the six current exponentials of br.py:150-157 are all e^{0.04 V0} times a constant;
+//   * r = d0 + sum d_i S_i with S_i = 2^{i-1} x^i is the ordinary polynomial sum c_i x^i,
+//     c_i = d_i 2^{i-1} (exact scaling), evaluated by Horner's scheme with FMAs (8 per gate
+//     function).  This is MORE accurate than the reference's left-to-right
+//     fp32 sum in the ill-conditioned S basis; the two differ by the reference's own rounding
+//     error (recorded in the fixtures as meta['rounding']).
 #pragma once
 #include "fib_kernels.cuh"
+
+// tuning knobs, chosen by measurement on B200 (cells per thread, resident CTAs per SM): the
+// kernels are issue/latency bound, so occupancy beats per-thread vector width.  The step that also
+// advances the four slow gates holds more live values than the fast-only step of the skip schedule.
+#ifndef FIB_BR_VEC_SLOW
+#define FIB_BR_VEC_SLOW 1
+#endif
+#ifndef FIB_BR_MINB_SLOW
+#define FIB_BR_MINB_SLOW 8
+#endif
+#ifndef FIB_BR_VEC_FAST
+#define FIB_BR_VEC_FAST 2
+#endif
+#ifndef FIB_BR_MINB_FAST
+#define FIB_BR_MINB_FAST 6
+#endif
 
 namespace fib {
 
@@ -10,16 +35,19 @@ namespace fib {
 // coefficients only, so every `== 0` test below folds at compile time (exp(0) == 1 exactly).
 __device__ __forceinline__ float br_rate(float v, float c0, float c1, float c2, float c3, float c4,
                                          float c5, float c6) {
-  const float e_num = (c1 == 0.f) ? 1.f : expf(c1 * (v + c2));
+  const float e_num = (c1 == 0.f) ? 1.f : m_exp(c1 * (v + c2));
   float num = (c0 == 0.f) ? 0.f : c0 * e_num;
   if (c3 != 0.f) num = (c0 == 0.f) ? c3 * (v + c4) : num + c3 * (v + c4);
-  const float e_den = (c5 == 0.f) ? 1.f : expf(c5 * (v + c2));
-  return num / (e_den + c6);
+  if (c5 == 0.f) return num * (1.0f / (1.0f + c6));
+  // e^z - 1 (alpha_m, removable singularity at -47 mV) goes through expm1
+  if (c6 == -1.f) return m_div(num, m_expm1(c5 * (v + c2)));
+  return m_div(num, m_exp(c5 * (v + c2)) + c6);
 }
 
-// gate order: 0 xi, 1 m, 2 h, 3 j, 4 d, 5 f  (br.py:285-286); d/f rates doubled (br.py:46-48)
+// gate order: 0 xi, 1 m, 2 h, 3 j, 4 d, 5 f  (br.py:285-286); d/f rates doubled (br.py:46-48).
+// Returns inf = a/(a+b) and rate = a+b = 1/tau (br.py:266-273).
 template <int G>
-__device__ __forceinline__ void br_inf_tau_exact(float v, float& inf, float& tau) {
+__device__ __forceinline__ void br_inf_rate_exact(float v, float& inf, float& rate) {
   float a, b;
   if (G == 0) { a = br_rate(v, 0.0005f, 0.083f, 50.f, 0.f, 0.f, 0.057f, 1.f);
                 b = br_rate(v, 0.0013f, -0.06f, 20.f, 0.f, 0.f, -0.04f, 1.f); }
@@ -33,27 +61,36 @@ __device__ __forceinline__ void br_inf_tau_exact(float v, float& inf, float& tau
                 b = br_rate(v, (float)(2 * 0.07), -0.017f, 44.f, 0.f, 0.f, 0.05f, 1.f); }
   if (G == 5) { a = br_rate(v, (float)(2 * 0.012), -0.008f, 28.f, 0.f, 0.f, 0.15f, 1.f);
                 b = br_rate(v, (float)(2 * 0.0065), -0.02f, 30.f, 0.f, 0.f, -0.2f, 1.f); }
-  const float ab = a + b;
-  inf = a / ab;          // br.py:273
-  tau = 1.0f / ab;
+  rate = a + b;
+  inf = m_div(a, rate);
 }
 
-// r = d0 + d1 S1 + ... + d8 S8, left to right, each product and sum rounded (br.py:327-331).
-// Uncontracted on purpose: the scaled-monomial basis is ill-conditioned, so an FMA's missing
-// rounding is amplified well above 1 ulp; the reference's fp32 NumPy/TF evaluation is the target.
-__device__ __forceinline__ float br_cheby_eval(const float* __restrict__ d, const float (&S)[9]) {
-  float r = __fadd_rn(d[0], __fmul_rn(d[1], S[1]));
+// rush_larsen with tau given as its reciprocal: expm1(-dt/tau) = expm1(-dt * rate)
+__device__ __forceinline__ float rush_larsen_rate(float g, float g_inf, float rate, float neg_dt) {
+  return rush_larsen_e(g, g_inf, m_expm1(neg_dt * rate));
+}
+__device__ __forceinline__ float rush_larsen_rate_slow(float g, float g_inf, float rate, float neg_dt) {
+  return rush_larsen_e(g, g_inf, m_expm1_small(neg_dt * rate));
+}
+
+// Horner evaluation of c0 + c1 x + ... + c8 x^8.  Every FMA has exactly ONE constant-bank operand
+// (the coefficient lives in the kernel parameter bank), so no LDC is needed; Estrin's scheme was
+// measured slower because its two-constant FMAs saturate the ADU pipe with constant loads.  The
+// 12 gate functions are independent chains, which is all the ILP the scheduler needs.
+__device__ __forceinline__ float br_poly8(const float* __restrict__ c, float x) {
+  float r = c[8];
 #pragma unroll
-  for (int i = 2; i < 9; ++i) r = __fadd_rn(r, __fmul_rn(d[i], S[i]));
+  for (int i = 7; i >= 0; --i) r = fmaf(r, x, c[i]);
   return r;
 }
 
 template <bool CHEBY, bool SLOW>
 struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
-  static constexpr int VEC = 4;
+  static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
   static constexpr int BY = 4;
-  static constexpr int MAX_R = 4;
+  static constexpr int MAX_R = 2;
+  static constexpr int MIN_BLOCKS = SLOW ? FIB_BR_MINB_SLOW : FIB_BR_MINB_FAST;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
   static constexpr bool NEED_LAP = true;
   static constexpr bool STORE_X = true;
@@ -65,7 +102,7 @@ struct BeelerReuter {
     float neg_dt;        // fp32(-dt)                  m, h
     float neg_dt_slow;   // fp32(-(dt*n))              xi, j, d, f when n > 0 (br.py:197-200)
     float ddt;           // fp32(diff*dt)
-    float cheb[12][9];   // FIB_TABLE_BR_CHEBY (only read when CHEBY)
+    float poly[12][9];   // FIB_TABLE_BR_CHEBY re-expressed as monomial coefficients c_i = d_i 2^(i-1)
   };
   static __device__ __forceinline__ void prologue(const StepArgs<BeelerReuter>&) {}
 
@@ -74,51 +111,70 @@ struct BeelerReuter {
     const Params& p = a.p;
     const float C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
 
-    float inf[6], tau[6];
     if (CHEBY) {
-      // x = (V0 - 0.5(max+min)) / (0.5(max-min)) = (V0 + 30)/60  (br.py:215), S_i = 2x S_{i-1}
-      const float x = __fdiv_rn(V0 + 30.0f, 60.0f);
-      const float x2 = 2.0f * x;
-      float S[9];
-      S[0] = 1.f; S[1] = x;
-#pragma unroll
-      for (int i = 2; i < 9; ++i) S[i] = __fmul_rn(x2, S[i - 1]);
-#pragma unroll
-      for (int g = 0; g < 6; ++g) {
-        if (g == 1 || g == 2 || SLOW) {
-          inf[g] = br_cheby_eval(p.cheb[2 * g], S);
-          tau[g] = br_cheby_eval(p.cheb[2 * g + 1], S);
-        }
-      }
-    } else {
-      br_inf_tau_exact<1>(V0, inf[1], tau[1]);
-      br_inf_tau_exact<2>(V0, inf[2], tau[2]);
+      // x = (V0 - 0.5(max+min)) / (0.5(max-min)) = (V0 + 30)/60   (br.py:215)
+      const float x = (V0 + 30.0f) * (1.0f / 60.0f);
+#define FIB_BR_GATE(RL, g, idx, ndt) \
+  s[idx] = RL(s[idx], br_poly8(p.poly[2 * (g)], x), br_poly8(p.poly[2 * (g) + 1], x), ndt)
+      FIB_BR_GATE(rush_larsen, 1, 1, p.neg_dt);                 // m: dt/tau_m is O(1..10)
+      FIB_BR_GATE(rush_larsen_slow, 2, 2, p.neg_dt);            // h
       if (SLOW) {
-        br_inf_tau_exact<0>(V0, inf[0], tau[0]);
-        br_inf_tau_exact<3>(V0, inf[3], tau[3]);
-        br_inf_tau_exact<4>(V0, inf[4], tau[4]);
-        br_inf_tau_exact<5>(V0, inf[5], tau[5]);
+        FIB_BR_GATE(rush_larsen_slow, 0, 6, p.neg_dt_slow);     // xi
+        FIB_BR_GATE(rush_larsen_slow, 3, 3, p.neg_dt_slow);     // j
+        FIB_BR_GATE(rush_larsen_slow, 4, 4, p.neg_dt_slow);     // d
+        FIB_BR_GATE(rush_larsen_slow, 5, 5, p.neg_dt_slow);     // f
       }
-    }
-    s[1] = rush_larsen(M, inf[1], tau[1], p.neg_dt);
-    s[2] = rush_larsen(H, inf[2], tau[2], p.neg_dt);
-    if (SLOW) {
-      s[6] = rush_larsen(XI, inf[0], tau[0], p.neg_dt_slow);
-      s[3] = rush_larsen(J, inf[3], tau[3], p.neg_dt_slow);
-      s[4] = rush_larsen(D, inf[4], tau[4], p.neg_dt_slow);
-      s[5] = rush_larsen(F, inf[5], tau[5], p.neg_dt_slow);
+#undef FIB_BR_GATE
+    } else {
+      float inf, rate;
+      br_inf_rate_exact<1>(V0, inf, rate); s[1] = rush_larsen_rate(M, inf, rate, p.neg_dt);
+      br_inf_rate_exact<2>(V0, inf, rate); s[2] = rush_larsen_rate_slow(H, inf, rate, p.neg_dt);
+      if (SLOW) {
+        br_inf_rate_exact<0>(V0, inf, rate); s[6] = rush_larsen_rate_slow(XI, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<3>(V0, inf, rate); s[3] = rush_larsen_rate_slow(J, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<4>(V0, inf, rate); s[4] = rush_larsen_rate_slow(D, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<5>(V0, inf, rate); s[5] = rush_larsen_rate_slow(F, inf, rate, p.neg_dt_slow);
+      }
     }
 
-    // currents from V0 and the OLD gates (br.py:150-165)
-    const float iK1 = 0.35f * (4.f * (expf(0.04f * (V0 + 85.f)) - 1.f) /
-                                   (expf(0.08f * (V0 + 53.f)) + expf(0.04f * (V0 + 53.f))) +
-                               0.2f * ((V0 + 23.0f) / (1.0f - expf(-0.04f * (V0 + 23.f)))));
-    const float ix1 = XI * 0.8f * (expf(0.04f * (V0 + 77.f)) - 1.f) / expf(0.04f * (V0 + 35.f));
+    // currents from V0 and the OLD gates (br.py:150-165); k = e^{0.04 V0}
+    constexpr float E85 = 29.96410004739701f;    // e^{0.04*85}
+    constexpr float E53 = 8.331137487687693f;     // e^{0.04*53}
+    constexpr float E77 = 21.75840239619708f;    // e^{0.04*77}
+    constexpr float E35 = 4.055199966844675f;    // e^{0.04*35}
+    const float k = m_exp(0.04f * V0);
+    const float k53 = k * E53;
+    const float d23 = V0 + 23.0f;
+    // (V0+23) / (1 - e^{-0.04 (V0+23)}): removable singularity at -23 mV.  Away from it
+    // 1 - e^{-0.92}/k is accurate and free (k is already known); within +-6 mV the expm1
+    // polynomial takes over (warp-uniform branch, rarely taken).
+    constexpr float E23N = 0.3985190410845142f;   // e^{-0.04*23}
+    float one_m_e = fmaf(-E23N, m_rcp(k), 1.0f);
+    {
+      const float z = -0.04f * d23;
+      const bool near = fabsf(z) < 0.25f;
+      if (__any_sync(__activemask(), near)) {
+        float q = 1.98412698412698e-4f;
+        q = fmaf(q, z, 1.38888888888889e-3f);
+        q = fmaf(q, z, 8.33333333333333e-3f);
+        q = fmaf(q, z, 4.16666666666667e-2f);
+        q = fmaf(q, z, 1.66666666666667e-1f);
+        q = fmaf(q, z, 0.5f);
+        q = fmaf(q * z, z, z);                    // expm1(z)
+        one_m_e = near ? -q : one_m_e;
+      }
+    }
+    const float sing = m_div(d23, one_m_e);
+    const float iK1 = 0.35f * (m_div(4.f * fmaf(k, E85, -1.f), fmaf(k53, k53, k53)) + 0.2f * sing);
+    const float ix1 = XI * 0.8f * m_div(fmaf(k, E77, -1.f), k * E35);
     const float iNa = (4.0f * M * M * M * H * J + 0.005f) * (V0 - 50.0f);
-    const float ECa = -82.3f - 13.0278f * logf(C);
+    const float ECa = -82.3f - 13.0278f * m_log(C);
     const float iCa = 0.09f * D * F * (V0 - ECa);
     const float I_sum = iK1 + ix1 + iNa + iCa;
-    Vnew = clip_nan(fmaf(p.ddt, lap, V0) - p.dt * I_sum, -85.0f, 25.0f);
+    // (V0 + ddt*lap) - dt*I_sum/C_m with the reference's rounding sequence (br.py:167-168): the
+    // result crosses 0 mV while the operands are ~80 mV, so no FMA contraction here
+    Vnew = clip_nan(__fsub_rn(__fadd_rn(V0, __fmul_rn(p.ddt, lap)), __fmul_rn(p.dt, I_sum)), -85.0f,
+                    25.0f);
     const float dC = -1.0e-7f * iCa + 0.07f * (1.0e-7f - C);
     s[0] = fmaf(p.dt, dC, C);
   }

@@ -5,11 +5,23 @@
 #pragma once
 #include "fib_kernels.cuh"
 
+// resident CTAs per SM the register allocator must leave room for, per kernel flavour (measured)
+#ifndef FIB_COURT_MINB_FAST
+#define FIB_COURT_MINB_FAST 12
+#endif
+#ifndef FIB_COURT_MINB_ALL
+#define FIB_COURT_MINB_ALL 8
+#endif
+#ifndef FIB_COURT_MINB_LUT
+#define FIB_COURT_MINB_LUT 5
+#endif
+
 namespace fib {
 
 constexpr int kLutRows = 150;   // ionic.h:47  TABLE_ROWS
 constexpr int kLutCols = 30;    // ionic.h:48  TABLE_COLS
 constexpr int kInterCols = 32;  // 30 LUT columns + us_infinity, tau_us
+constexpr int kLutTStride = 160;  // row stride of the device-side TRANSPOSED table [30][160]
 
 // column order of courtemanche.h:105-134
 enum CourtQ {
@@ -45,114 +57,119 @@ template <bool WANT_US>
 __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols]) {
   using namespace cc;
   const float eps = V * 1e-20f;
-  q[Q_d_inf] = 1.0f / (1.0f + expf((V + 10.0f) * -0.125f));
+  q[Q_d_inf] = m_rcp(1.0f + m_exp((V + 10.0f) * -0.125f));
   {
     const float w = V + 10.0001f;
-    const float e = expf(w * -FIB_RCPF(6.24));
+    const float e = m_exp(w * -FIB_RCPF(6.24));
     q[Q_tau_d] = fabsf(w) < 1.0e-10f
                      ? 4.579f / (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24)))
-                     : (1.0f - e) / (0.0350000f * w * (1.0f + e));
+                     : m_div(1.0f - e, 0.0350000f * w * (1.0f + e));
   }
   {
-    const float e = expf(-(V + 28.0f) * FIB_RCPF(6.9));
-    q[Q_f_inf] = e / (1.0f + e);
+    const float e = m_exp(-(V + 28.0f) * FIB_RCPF(6.9));
+    q[Q_f_inf] = m_div(e, 1.0f + e);
   }
   {
     const float a = (V + 10.0f);
-    q[Q_tau_f] = 9.0f * (1.0f / (0.0197000f * expf(-(0.0337f * 0.0337f) * (a * a)) + 0.02f));
+    q[Q_tau_f] = 9.0f * m_rcp(0.0197000f * m_exp(-(0.0337f * 0.0337f) * (a * a)) + 0.02f);
   }
   {
     const float w = V - 7.9f;
-    const float e = expf(-w * 0.2f);
+    const float e = m_exp(-w * 0.2f);
     q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)((6.0 * 0.2) / 1.3)
-                                     : (6.0f * (1.0f - e)) / ((1.0f + 0.3f * e) * 1.0f * w);
+                                     : m_div(6.0f * (1.0f - e), (1.0f + 0.3f * e) * 1.0f * w);
   }
-  q[Q_w_inf] = 1.0f - 1.0f / (1.0f + expf(-(V - 40.0f) * FIB_RCPF(17.0)));
+  q[Q_w_inf] = 1.0f - m_rcp(1.0f + m_exp(-(V - 40.0f) * FIB_RCPF(17.0)));
   {
     const float w = V + 47.13f;
-    const float alpha_m = fabsf(V - -47.13f) < 0.001f ? 3.2f : (0.32f * w) / (1.0f - expf(-0.1f * w));
-    const float beta_m = 0.08f * expf(-V * FIB_RCPF(11.0));
-    q[Q_m_inf] = alpha_m / (alpha_m + beta_m);
-    q[Q_tau_m] = 1.0f / (alpha_m + beta_m);
+    const float alpha_m =
+        fabsf(V - -47.13f) < 0.001f ? 3.2f : m_div(0.32f * w, 1.0f - m_exp(-0.1f * w));
+    const float beta_m = 0.08f * m_exp(-V * FIB_RCPF(11.0));
+    const float r = m_rcp(alpha_m + beta_m);
+    q[Q_m_inf] = alpha_m * r;
+    q[Q_tau_m] = r;
   }
   const bool lo = V < -40.0f;
   {
-    const float alpha_h = lo ? 0.135f * expf((V + 80.0f) * -FIB_RCPF(6.8)) : eps;
-    const float beta_h = lo ? 3.56f * expf(0.079f * V) + 310000.f * expf(0.35f * V)
-                            : 1.0f / (0.13f * (1.0f + expf((V + 10.66f) * -FIB_RCPF(11.1))));
-    q[Q_h_inf] = alpha_h / (alpha_h + beta_h);
-    q[Q_tau_h] = 1.0f / (alpha_h + beta_h);
+    const float alpha_h = lo ? 0.135f * m_exp((V + 80.0f) * -FIB_RCPF(6.8)) : eps;
+    const float beta_h = lo ? 3.56f * m_exp(0.079f * V) + 310000.f * m_exp(0.35f * V)
+                            : m_rcp(0.13f * (1.0f + m_exp((V + 10.66f) * -FIB_RCPF(11.1))));
+    const float r = m_rcp(alpha_h + beta_h);
+    q[Q_h_inf] = alpha_h * r;
+    q[Q_tau_h] = r;
   }
   {
     const float alpha_j =
-        lo ? ((-127140.f * expf(0.2444f * V) - 3.474e-05f * expf(-0.04391f * V)) * (V + 37.78f)) /
-                 (1.0f + expf(0.311f * (V + 79.23f)))
+        lo ? m_div((-127140.f * m_exp(0.2444f * V) - 3.474e-05f * m_exp(-0.04391f * V)) * (V + 37.78f),
+                   1.0f + m_exp(0.311f * (V + 79.23f)))
            : eps;
-    const float beta_j = lo ? (0.1212f * expf(-0.01052f * V)) / (1.0f + expf(-0.1378f * (V + 40.14f)))
-                            : (0.3f * expf(-2.535e-07f * V)) / (1.0f + expf(-0.1f * (V + 32.0f)));
-    q[Q_j_inf] = alpha_j / (alpha_j + beta_j);
-    q[Q_tau_j] = 1.0f / (alpha_j + beta_j);
+    const float beta_j = lo ? m_div(0.1212f * m_exp(-0.01052f * V), 1.0f + m_exp(-0.1378f * (V + 40.14f)))
+                            : m_div(0.3f * m_exp(-2.535e-07f * V), 1.0f + m_exp(-0.1f * (V + 32.0f)));
+    const float r = m_rcp(alpha_j + beta_j);
+    q[Q_j_inf] = alpha_j * r;
+    q[Q_tau_j] = r;
   }
   const float Vs = V - -10.0f;
   {
     // alpha/beta of oa and ua are the same expressions (court.py:363-364, 375-376)
-    const float alpha = 0.65f * (1.0f / (expf(Vs * -FIB_RCPF(8.5)) + expf((Vs - 40.0f) * -FIB_RCPF(59.0))));
-    const float beta = 0.65f * (1.0f / (2.5f + expf((Vs + 72.0f) * FIB_RCPF(17.0))));
-    const float t = (1.0f / (alpha + beta)) * FIB_RCPF(3.0);
+    const float alpha = 0.65f * m_rcp(m_exp(Vs * -FIB_RCPF(8.5)) + m_exp((Vs - 40.0f) * -FIB_RCPF(59.0)));
+    const float beta = 0.65f * m_rcp(2.5f + m_exp((Vs + 72.0f) * FIB_RCPF(17.0)));
+    const float t = m_rcp(alpha + beta) * FIB_RCPF(3.0);
     q[Q_tau_oa] = t;
     q[Q_tau_ua] = t;
   }
-  q[Q_oa_inf] = 1.0f / (1.0f + expf((Vs + 10.47f) * -FIB_RCPF(17.54)));
+  q[Q_oa_inf] = m_rcp(1.0f + m_exp((Vs + 10.47f) * -FIB_RCPF(17.54)));
   {
-    const float alpha = 1.0f / (18.53f + 1.0f * expf((Vs + 103.7f) * FIB_RCPF(10.95)));
-    const float beta = 1.0f / (35.56f + 1.0f * expf((Vs - 8.74f) * -FIB_RCPF(7.44)));
-    q[Q_tau_oi] = (1.0f / (alpha + beta)) * FIB_RCPF(3.0);
+    const float alpha = m_rcp(18.53f + 1.0f * m_exp((Vs + 103.7f) * FIB_RCPF(10.95)));
+    const float beta = m_rcp(35.56f + 1.0f * m_exp((Vs - 8.74f) * -FIB_RCPF(7.44)));
+    q[Q_tau_oi] = m_rcp(alpha + beta) * FIB_RCPF(3.0);
   }
-  q[Q_oi_inf] = 1.0f / (1.0f + expf((Vs + 33.1f) * FIB_RCPF(5.3)));
-  q[Q_ua_inf] = 1.0f / (1.0f + expf((Vs + 20.3f) * -FIB_RCPF(9.6)));
+  q[Q_oi_inf] = m_rcp(1.0f + m_exp((Vs + 33.1f) * FIB_RCPF(5.3)));
+  q[Q_ua_inf] = m_rcp(1.0f + m_exp((Vs + 20.3f) * -FIB_RCPF(9.6)));
   {
-    const float alpha = 1.0f / (21.0f + 1.0f * expf((Vs - 195.000f) * -FIB_RCPF(28.0)));
-    const float beta = 1.0f / expf((Vs - 168.0f) * -0.0625f);
-    q[Q_tau_ui] = (1.0f / (alpha + beta)) * FIB_RCPF(3.0);
+    const float alpha = m_rcp(21.0f + 1.0f * m_exp((Vs - 195.000f) * -FIB_RCPF(28.0)));
+    const float beta = m_exp((Vs - 168.0f) * 0.0625f);          // 1 / e^{-z} = e^{z}
+    q[Q_tau_ui] = m_rcp(alpha + beta) * FIB_RCPF(3.0);
   }
-  q[Q_ui_inf] = 1.0f / (1.0f + expf((Vs - 109.45f) * FIB_RCPF(27.48)));
+  q[Q_ui_inf] = m_rcp(1.0f + m_exp((Vs - 109.45f) * FIB_RCPF(27.48)));
   {
     const float w = V + 14.1f;
-    const float alpha = fabsf(w) < 1.0e-10f ? 0.0015f : (0.0003f * w) / (1.0f - expf(w * -0.2f));
+    const float alpha = fabsf(w) < 1.0e-10f ? 0.0015f : m_div(0.0003f * w, 1.0f - m_exp(w * -0.2f));
     const float z = V - 3.3328f;
     const float beta = fabsf(z) < 1.0e-10f
                            ? 0.000378361f
-                           : (7.3898e-05f * z) / (expf(z * FIB_RCPF(5.1237)) - 1.0f);
-    q[Q_tau_xr] = 1.0f / (alpha + beta);
-    q[Q_xr_inf] = 1.0f / (1.0f + expf(w * -FIB_RCPF(6.5)));
+                           : m_div(7.3898e-05f * z, m_exp(z * FIB_RCPF(5.1237)) - 1.0f);
+    q[Q_tau_xr] = m_rcp(alpha + beta);
+    q[Q_xr_inf] = m_rcp(1.0f + m_exp(w * -FIB_RCPF(6.5)));
   }
   {
     const float w = V - 19.9f;
     const bool z = fabsf(w) < 1.0e-10f;
-    const float alpha = z ? 0.00068f : (4.0e-05f * w) / (1.0f - expf(w * -FIB_RCPF(17.0)));
-    const float beta = z ? 0.000315f : (3.5e-05f * w) / (expf(w * FIB_RCPF(9.0)) - 1.0f);
-    q[Q_tau_xs] = 0.5f * (1.0f / (alpha + beta));
-    q[Q_xs_inf] = sqrtf(1.0f / (1.0f + expf(w * -FIB_RCPF(12.7))));
+    const float alpha = z ? 0.00068f : m_div(4.0e-05f * w, 1.0f - m_exp(w * -FIB_RCPF(17.0)));
+    const float beta = z ? 0.000315f : m_div(3.5e-05f * w, m_exp(w * FIB_RCPF(9.0)) - 1.0f);
+    q[Q_tau_xs] = 0.5f * m_rcp(alpha + beta);
+    q[Q_xs_inf] = m_sqrt(m_rcp(1.0f + m_exp(w * -FIB_RCPF(12.7))));
   }
-  q[Q_g_Kur] = 0.005f + 0.05f / (1.0f + expf((V - 15.0f) * -FIB_RCPF(13.0)));
+  q[Q_g_Kur] = 0.005f + 0.05f * m_rcp(1.0f + m_exp((V - 15.0f) * -FIB_RCPF(13.0)));
   {
     constexpr float rRT = FIB_RCPF(R * T);
-    q[Q_f_NaK] = 1.0f / (1.0f + 0.1245f * expf(((float)(-0.1 * F) * V) * rRT) +
-                         (float)(0.0365 * sigma) * expf(((float)(-F) * V) * rRT));
-    const float eg1 = expf((((float)(gamma_ - 1.0) * V) * (float)F) * rRT);
-    const float d = (float)((K_mNa * K_mNa * K_mNa + Na_o * Na_o * Na_o) * (K_mCa + Ca_o)) *
-                    (1.0f + (float)K_sat * eg1);
-    q[Q_i_NaCaa] = ((float)(Cm * I_NaCa_max) * (expf(((float)(gamma_ * F) * V) * rRT) * (float)Ca_o)) / d;
-    q[Q_i_NaCab] = ((float)(Cm * I_NaCa_max) *
-                    (expf(((float)((gamma_ - 1.0) * F) * V) * rRT) * (float)(Na_o * Na_o * Na_o))) / d;
+    q[Q_f_NaK] = m_rcp(1.0f + 0.1245f * m_exp(((float)(-0.1 * F) * V) * rRT) +
+                       (float)(0.0365 * sigma) * m_exp(((float)(-F) * V) * rRT));
+    const float eg1 = m_exp((((float)(gamma_ - 1.0) * V) * (float)F) * rRT);
+    const float rd = m_rcp((float)((K_mNa * K_mNa * K_mNa + Na_o * Na_o * Na_o) * (K_mCa + Ca_o)) *
+                           (1.0f + (float)K_sat * eg1));
+    q[Q_i_NaCaa] = ((float)(Cm * I_NaCa_max) * (m_exp(((float)(gamma_ * F) * V) * rRT) * (float)Ca_o)) * rd;
+    // e^{(gamma-1) F V / RT} is eg1 again (court.py:421 vs :417 differ only in operand order)
+    q[Q_i_NaCab] = ((float)(Cm * I_NaCa_max) * (eg1 * (float)(Na_o * Na_o * Na_o))) * rd;
   }
-  q[Q_i_K1a] = (float)(Cm * g_K1) / (1.0f + expf(0.07f * (V + 80.0f)));
-  q[Q_i_Kra] = (float)(Cm * g_Kr) / (1.0f + expf((V + 15.0f) * FIB_RCPF(22.4)));
+  q[Q_i_K1a] = (float)(Cm * g_K1) * m_rcp(1.0f + m_exp(0.07f * (V + 80.0f)));
+  q[Q_i_Kra] = (float)(Cm * g_Kr) * m_rcp(1.0f + m_exp((V + 15.0f) * FIB_RCPF(22.4)));
   if (WANT_US) {   // court_ultra.py:445-450
     const float a_us = 3e-5f * (0.5f * (1.f - tanhf((V - -83.0f) * FIB_RCPF(23.0))));
     const float b_us = 1e-5f * (0.5f * (1.f + tanhf((V - (float)(-83.0 + 30)) * FIB_RCPF(23.0))));
-    q[Q_us_inf] = a_us / (a_us + b_us);
-    q[Q_tau_us] = 1.0f / (a_us + b_us);
+    const float r = m_rcp(a_us + b_us);
+    q[Q_us_inf] = a_us * r;
+    q[Q_tau_us] = r;
   } else {
     q[Q_us_inf] = 0.f;
     q[Q_tau_us] = 1.f;
@@ -170,7 +187,9 @@ struct Courtemanche {
   static constexpr int NS = S_COUNT;      // 21 slots; S_us only used when US
   static constexpr int VEC = 1;
   static constexpr int BY = 4;
-  static constexpr int MAX_R = 2;
+  static constexpr int MAX_R = LUT ? 2 : 1;
+  static constexpr int MIN_BLOCKS =
+      MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
   static constexpr bool NEED_RAW = false; // V = enforce_boundary(V0) everywhere (court.py:126-127)
   static constexpr bool NEED_LAP = MODE != COURT_SLOW;
   static constexpr bool STORE_X = MODE != COURT_SLOW;
@@ -179,7 +198,7 @@ struct Courtemanche {
     return (k == S_us) ? (US && MODE != COURT_FAST)
                        : (MODE == COURT_ALL ? true : (MODE == COURT_FAST ? is_fast(k) : !is_fast(k)));
   }
-  static size_t smem_bytes() { return LUT ? sizeof(float) * kLutRows * kLutCols : 0; }
+  static size_t smem_bytes() { return 0; }
   struct Params {
     float dt_fast, neg_dt_fast;   // V, _Na_i_, _m_, _h_        (court.py:118-120)
     float dt_slow, neg_dt_slow;   // everything else: 10*dt for court.py, dt for court_ultra.py
@@ -190,15 +209,7 @@ struct Courtemanche {
                                   // on the host like the reference's Python (court.py:193-194,218)
   };
 
-  static __device__ __forceinline__ void prologue(const StepArgs<Courtemanche>& a) {
-    if (LUT) {
-      extern __shared__ float lut_s[];
-      for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < kLutRows * kLutCols;
-           i += blockDim.x * blockDim.y)
-        lut_s[i] = a.lut[i];
-      __syncthreads();
-    }
-  }
+  static __device__ __forceinline__ void prologue(const StepArgs<Courtemanche>&) {}
 
   static __device__ __forceinline__ void cell(const StepArgs<Courtemanche>& a, float /*raw*/,
                                               float V, float lap, float (&s)[NS], float& Vnew) {
@@ -206,12 +217,14 @@ struct Courtemanche {
     const Params& p = a.p;
     float q[kInterCols];
     if (LUT) {
-      extern __shared__ float lut_s[];
+      // The table is kept TRANSPOSED on the device ([column][voltage], 19 KB, L1-resident): the
+      // lanes of a warp sit within a few mV of each other, so each of the 30 column reads touches
+      // one or two 128-B lines instead of one line per distinct voltage row.
       int i = static_cast<int>(V + 100.f);           // courtemanche.h:354-356 (truncation)
       i = i < 0 ? 0 : (i >= kLutRows ? kLutRows - 1 : i);
-      const float* row = lut_s + i * kLutCols;
+      const float* col = a.lut + i;
 #pragma unroll
-      for (int k = 0; k < kLutCols; ++k) q[k] = row[k];
+      for (int k = 0; k < kLutCols; ++k) q[k] = __ldg(col + k * kLutTStride);
       if (US) {
         float qq[kInterCols];
         court_inter_dev<true>(V, qq);                // not tabulated in the reference
@@ -229,42 +242,42 @@ struct Courtemanche {
                 u = s[S_u], v = s[S_v], w = s[S_w];
 
     // gates (court.py:175-189); _w_ is clocked with the step of '_d_' (court.py:177) = slow
-    s[S_d] = rush_larsen(d, q[Q_d_inf], q[Q_tau_d], nds);
-    s[S_f] = rush_larsen(f, q[Q_f_inf], q[Q_tau_f], nds);
-    s[S_w] = rush_larsen(w, q[Q_w_inf], q[Q_tau_w], nds);
+    s[S_d] = rush_larsen_slow(d, q[Q_d_inf], q[Q_tau_d], nds);
+    s[S_f] = rush_larsen_slow(f, q[Q_f_inf], q[Q_tau_f], nds);
+    s[S_w] = rush_larsen_slow(w, q[Q_w_inf], q[Q_tau_w], nds);
     s[S_m] = rush_larsen(m, q[Q_m_inf], q[Q_tau_m], ndf);
-    s[S_h] = rush_larsen(h, q[Q_h_inf], q[Q_tau_h], ndf);
-    s[S_j] = rush_larsen(j, q[Q_j_inf], q[Q_tau_j], nds);
-    s[S_oa] = rush_larsen(oa, q[Q_oa_inf], q[Q_tau_oa], nds);
-    s[S_oi] = rush_larsen(oi, q[Q_oi_inf], q[Q_tau_oi], nds);
-    s[S_ua] = rush_larsen(ua, q[Q_ua_inf], q[Q_tau_ua], nds);
-    s[S_ui] = rush_larsen(ui, q[Q_ui_inf], q[Q_tau_ui], nds);
-    s[S_xr] = rush_larsen(xr, q[Q_xr_inf], q[Q_tau_xr], nds);
-    s[S_xs] = rush_larsen(xs, q[Q_xs_inf], q[Q_tau_xs], nds);
-    const float f_Ca_inf = 1.0f / (1.0f + Ca_i * FIB_RCPF(0.00035));
+    s[S_h] = rush_larsen_slow(h, q[Q_h_inf], q[Q_tau_h], ndf);
+    s[S_j] = rush_larsen_slow(j, q[Q_j_inf], q[Q_tau_j], nds);
+    s[S_oa] = rush_larsen_slow(oa, q[Q_oa_inf], q[Q_tau_oa], nds);
+    s[S_oi] = rush_larsen_slow(oi, q[Q_oi_inf], q[Q_tau_oi], nds);
+    s[S_ua] = rush_larsen_slow(ua, q[Q_ua_inf], q[Q_tau_ua], nds);
+    s[S_ui] = rush_larsen_slow(ui, q[Q_ui_inf], q[Q_tau_ui], nds);
+    s[S_xr] = rush_larsen_slow(xr, q[Q_xr_inf], q[Q_tau_xr], nds);
+    s[S_xs] = rush_larsen_slow(xs, q[Q_xs_inf], q[Q_tau_xs], nds);
+    const float f_Ca_inf = m_rcp(1.0f + Ca_i * FIB_RCPF(0.00035));
     s[S_f_Ca] = rush_larsen_e(f_Ca, f_Ca_inf, p.e_fCa);
     float us = 1.f;
     if (US) {
       us = s[S_us];
-      s[S_us] = rush_larsen(us, q[Q_us_inf], q[Q_tau_us], nds);   // court_ultra.py:198-199
+      s[S_us] = rush_larsen_slow(us, q[Q_us_inf], q[Q_tau_us], nds);   // court_ultra.py:198-199
     }
 
     // currents (court.py:191-221)
     constexpr float RTF = (float)((R * T) / F);
-    const float E_K = RTF * logf((float)K_o / K_i);
+    const float E_K = RTF * m_log(m_div((float)K_o, K_i));
     const float dVK = V - E_K;
     const float i_K1 = q[Q_i_K1a] * dVK;
     const float i_to = p.k_to * (oa * oa * oa) * oi * dVK;
     const float i_Kur = p.k_Kur * q[Q_g_Kur] * (ua * ua * ua) * ui * dVK;
     const float i_Kr = q[Q_i_Kra] * xr * dVK;
     const float i_Ks = (float)(Cm * g_Ks) * (xs * xs) * dVK;
-    const float r_na = (float)Km_Na_i / Na_i;
-    const float i_NaK = (((float)(Cm * i_NaK_max) * q[Q_f_NaK]) / (1.0f + sqrtf(r_na * r_na * r_na))) *
+    const float r_na = m_div((float)Km_Na_i, Na_i);
+    const float i_NaK = m_div((float)(Cm * i_NaK_max) * q[Q_f_NaK], 1.0f + m_sqrt(r_na * r_na * r_na)) *
                         (float)(K_o / (K_o + Km_K_o));
     // i_B_K = Cm * g_B_K * (V - E_K) with g_B_K = 0 (court.py:198): contributes +0
     s[S_K_i] = fmaf((2.0f * i_NaK - (i_K1 + i_to + i_Kur + i_Kr + i_Ks)) * FIB_RCPF(V_i * F), dts, K_i);
 
-    const float E_Na = RTF * logf((float)Na_o / Na_i);
+    const float E_Na = RTF * m_log(m_div((float)Na_o, Na_i));
     float i_Na = (float)(Cm * g_Na) * (m * m * m) * h * j * (V - E_Na);
     if (US) i_Na *= us;                                         // court_ultra.py:221-222
     const float i_NaCa = q[Q_i_NaCaa] * (Na_i * Na_i * Na_i) - q[Q_i_NaCab] * Ca_i;
@@ -272,36 +285,37 @@ struct Courtemanche {
     s[S_Na_i] = fmaf((-3.0f * i_NaK - (3.0f * i_NaCa + i_B_Na + i_Na)) * FIB_RCPF(V_i * F), dtf, Na_i);
 
     const float i_Ca_L = p.k_CaL * d * f * f_Ca * (V - 65.0f);
-    const float i_CaP = ((float)(Cm * i_CaP_max) * Ca_i) / (0.0005f + Ca_i);
-    const float E_Ca = (float)((R * T) / (2.0 * F)) * logf((float)Ca_o / Ca_i);
+    const float i_CaP = m_div((float)(Cm * i_CaP_max) * Ca_i, 0.0005f + Ca_i);
+    const float E_Ca = (float)((R * T) / (2.0 * F)) * m_log(m_div((float)Ca_o, Ca_i));
     const float i_B_Ca = (float)(Cm * g_B_Ca) * (V - E_Ca);
     const float I_tot = i_Na + i_K1 + i_to + i_Kur + i_Kr + i_Ks + i_B_Na + i_B_Ca + i_NaK + i_CaP +
                         i_NaCa + i_Ca_L;
-    const float DV = fmaf(__fdiv_rn(-I_tot, (float)Cm), dtf, V);   // court.py:223-227
-    Vnew = fmaf(p.ddt, lap, DV);                                  // court.py:229
+    // reference rounding sequence, no FMA contraction (V crosses 0 mV with ~80 mV operands)
+    const float DV = __fadd_rn(V, __fmul_rn(__fdiv_rn(-I_tot, (float)Cm), dtf));   // court.py:223-227
+    Vnew = __fadd_rn(DV, __fmul_rn(p.ddt, lap));                                     // court.py:229
 
     // Ca handling (court.py:232-265)
     const float i_rel = (float)K_rel * (u * u) * v * w * (Ca_rel - Ca_i);
     const float i_tr = (Ca_up - Ca_rel) * FIB_RCPF(tau_tr);
     {
       const float z = Ca_rel + (float)Km_CSQN;
-      s[S_Ca_rel] = fmaf((i_tr - i_rel) * (1.0f / (1.0f + (float)(CSQN_max * Km_CSQN) / (z * z))), dts, Ca_rel);
+      s[S_Ca_rel] = fmaf((i_tr - i_rel) * m_rcp(1.0f + m_div((float)(CSQN_max * Km_CSQN), z * z)), dts, Ca_rel);
     }
     const float Fn = 1000.0f * ((float)(1.0e-15 * V_rel) * i_rel -
                                 (float)(1.0e-15 / (2.0 * F)) * (0.5f * i_Ca_L - 0.2f * i_NaCa));
-    const float u_inf = 1.0f / (1.0f + expf(-(Fn - 3.4175e-13f) * FIB_RCPF(1.367e-15)));
+    const float u_inf = m_rcp(1.0f + m_exp(-(Fn - 3.4175e-13f) * FIB_RCPF(1.367e-15)));
     s[S_u] = rush_larsen_e(u, u_inf, p.e_u);
     const float tau_v = 1.91f + 2.09f * u_inf;
-    const float v_inf = 1.0f - 1.0f / (1.0f + expf(-(Fn - 6.835e-14f) * FIB_RCPF(1.367e-15)));
+    const float v_inf = 1.0f - m_rcp(1.0f + m_exp(-(Fn - 6.835e-14f) * FIB_RCPF(1.367e-15)));
     s[S_v] = rush_larsen(v, v_inf, tau_v, nds);
-    const float i_up = (float)I_up_max / (1.0f + (float)K_up / Ca_i);
+    const float i_up = (float)I_up_max * m_rcp(1.0f + m_div((float)K_up, Ca_i));
     const float i_up_leak = ((float)I_up_max * Ca_up) * FIB_RCPF(Ca_up_max);
     s[S_Ca_up] = fmaf(i_up - (i_up_leak + (i_tr * (float)V_rel) * FIB_RCPF(V_up)), dts, Ca_up);
     const float B1 = (2.0f * i_NaCa - (i_CaP + i_Ca_L + i_B_Ca)) * FIB_RCPF(2.0 * V_i * F) +
                      ((float)V_up * (i_up_leak - i_up) + i_rel * (float)V_rel) * FIB_RCPF(V_i);
     const float zt = Ca_i + (float)Km_TRPN, zc = Ca_i + (float)Km_CMDN;
-    const float B2 = 1.0f + (float)(TRPN_max * Km_TRPN) / (zt * zt) + (float)(CMDN_max * Km_CMDN) / (zc * zc);
-    s[S_Ca_i] = fmaf(B1 / B2, dts, Ca_i);
+    const float B2 = 1.0f + m_div((float)(TRPN_max * Km_TRPN), zt * zt) + m_div((float)(CMDN_max * Km_CMDN), zc * zc);
+    s[S_Ca_i] = fmaf(m_div(B1, B2), dts, Ca_i);
   }
 };
 

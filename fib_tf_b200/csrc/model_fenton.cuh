@@ -3,13 +3,18 @@
 #pragma once
 #include "fib_kernels.cuh"
 
+#ifndef FIB_4V_MINB
+#define FIB_4V_MINB 7
+#endif
+
 namespace fib {
 
 struct Fenton4v {
   static constexpr int NS = 3;            // V, W, S  (U is the diffusing variable)
   static constexpr int VEC = 4;
   static constexpr int BY = 4;
-  static constexpr int MAX_R = 8;
+  static constexpr int MAX_R = 4;
+  static constexpr int MIN_BLOCKS = FIB_4V_MINB;
   static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
   static constexpr bool NEED_LAP = true;
   static constexpr bool STORE_X = true;
@@ -41,16 +46,19 @@ struct Fenton4v {
 
     const float I_fi = (-V * Hc) * (U - u_c) * (u_m - U) * (1.0f / tau_d);
     const float I_si = (-W * S) * (1.0f / tau_si);
-    const float I_so = c_so_half * (1.f + tanhf((U - b_so) * (1.0f / c_so))) +
+    // 0.5 (a_so - tau_a) (1 + tanh z) = (a_so - tau_a) * [0.5 (1 + tanh z)]
+    const float I_so = (2.0f * c_so_half) * m_half_1p_tanh((U - b_so) * (1.0f / c_so)) +
                        (U * Gso) * (1.0f / tau_so) + Hso * tau_a;
     const float dU = -(I_fi + I_si + I_so);
     const float dV = U > u_c ? -V * (1.0f / tau_vp) : (1.f - V) * (1.0f / tau_vn);
     // tau_wn1 == tau_wn2 == 75 (fenton.py:53-54): the inner tf.where is an identity
     const float dW = U > u_c ? -W * (1.0f / tau_wp) : (1.f - W) * (1.0f / tau_wn);
     const float r_s = fmaf(r_diff, Hc, r_sn);
-    const float dS = r_s * (0.5f * (1.f + tanhf((U - u_csi) * k_)) - S);
+    const float dS = r_s * (m_half_1p_tanh((U - u_csi) * k_) - S);
 
-    Unew = fmaf(a.p.ddt, lap, fmaf(dt, dU, U0));
+    // (U0 + dt*dU) + ddt*lap with the reference's rounding sequence (fenton.py:103): near U ~ 0 an
+    // FMA's missing rounding would show up as a 1-ulp(|U0|) absolute difference
+    Unew = __fadd_rn(__fadd_rn(U0, __fmul_rn(dt, dU)), __fmul_rn(a.p.ddt, lap));
     s[0] = fmaf(dt, dV, V);
     s[1] = fmaf(dt, dW, W);
     s[2] = fmaf(dt, dS, S);

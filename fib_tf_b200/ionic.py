@@ -225,8 +225,8 @@ class IonicModel:
                         image *= self.phase
                     im.imshow(image)
                     v1 = image[prow, pcol]
-                elif prow < self.height:
-                    v1 = self._probe_image(prow, pcol)
+                elif self._row0 <= prow < self._row0 + self._rows:
+                    v1 = self._probe_image(prow, pcol)      # headless: the owner rank watches
                 else:
                     continue
                 if v1 >= 0.5 and v0 < 0.5:
@@ -249,7 +249,7 @@ class IonicModel:
             im.wait()
 
     def _probe_image(self, row, col):
-        v = float(self._probe(self._pot_name, row, col))
+        v = float(self._ctx.probe(self._pot_name, row, col))
         v = self._normalise(v)
         if self.phase is not None and self._phase_row0 <= row < self._phase_row1:
             v *= float(self.phase[row - self._phase_row0, col])

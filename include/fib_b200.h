@@ -109,8 +109,10 @@ int         fib_dt_per_step(const fib_ctx *ctx);            /* model.dt_per_step
  * `n` must equal rows*width of THIS shard.  Synchronous. */
 int fib_set_state(fib_ctx *ctx, int var, const float *host, size_t n);
 int fib_get_state(fib_ctx *ctx, int var, float *host, size_t n);
-/* sub-rectangle read of the local shard (frame grabs / strided probes); global coordinates */
+/* sub-rectangle read / write of the local shard (frame grabs, strided probes, strip-wise upload
+ * of grids too large to stage on the host in one piece); global coordinates, dense host block */
 int fib_get_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float *host);
+int fib_set_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host);
 
 /* ---- phase field: replaces self.phi = tf.Variable(self.phase) (ionic.py:55-58) ---------
  * `rows_host` holds global rows [first_row, first_row+nrows) of the [H][W] phase field and must

@@ -27,7 +27,9 @@ Fixture layout (np.savez_compressed):
     trend           [n,2] fp32   (court.py only)
     meta['noise']   {'s{i}__{var}': e}: rel_err (oracle/monodomain_np.py) between two runs of the
                     unmodified reference that differ ONLY in the fp32 math library used for
-                    exp/expm1/log/tanh/pow (NumPy's vs correctly rounded) -- the noise floor.
+                    exp/expm1/log/tanh/pow (NumPy's vs correctly rounded) -- the libm noise.
+    meta['rounding'] same metric between the fp32 reference and the SAME graph evaluated in float64
+                    (fp32-rounded constants and inputs): the reference's total fp32 rounding error.
 """
 import json
 import os
@@ -86,9 +88,10 @@ def state_of(model, kind):
 
 
 def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=None,
-             s1=True, trend_op=False, _alt=False):
-    from oracle.monodomain_np import rel_err, var_scale
-    shim.ALT_LIBM = _alt
+             s1=True, trend_op=False, _alt=None):
+    from oracle.monodomain_np import rel_err, var_floor
+    shim.ALT_LIBM = _alt == 'libm'
+    shim.WIDE = _alt == 'wide'
     shim.reset_registry()
     model = MODELS[kind](cfg)
     for h in holes:
@@ -120,23 +123,28 @@ def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=
         sys.stdout.close()
         sys.stdout = sys.__stdout__
         shim.ALT_LIBM = False
+        shim.WIDE = False
     if _alt:
         return out
-    noise = {}
+    noise, rounding = {}, {}
     if probe is None:
         # second pass of the unmodified reference with the alternate fp32 libm: its deviation from
         # the first pass is the reference's own noise floor (see tfshim.ALT_LIBM)
         alt = run_case(name, kind, cfg, holes, paces, slow_every, snaps, probe, s1, trend_op,
-                       _alt=True)
+                       _alt='libm')
+        wide = run_case(name, kind, cfg, holes, paces, slow_every, snaps, probe, s1, trend_op,
+                        _alt='wide')
         for k in out:
             if k.startswith('s') and '__' in k:
-                noise[k] = rel_err(alt[k], out[k], var_scale(kind, k.split('__', 1)[1]))
+                fl = var_floor(kind, k.split('__', 1)[1])
+                noise[k] = rel_err(alt[k], out[k], fl)
+                rounding[k] = rel_err(wide[k], out[k], fl)
     meta = {
         'name': name, 'model': kind, 'config': cfg, 'holes': [list(h) for h in holes],
         'paces': [list(p) for p in paces], 'slow_every': slow_every,
         'snaps': sorted(snaps), 'probe': list(probe) if probe else None,
         'dt_per_step': model.dt_per_step, 'samples': model.samples, 's1': bool(s1),
-        'vars': sorted(state_of(model, kind).keys()), 'noise': noise,
+        'vars': sorted(state_of(model, kind).keys()), 'noise': noise, 'rounding': rounding,
         'generator': 'oracle/make_golden.py (unmodified reference under oracle/tfshim.py)',
         'numpy': np.__version__,
     }

@@ -33,6 +33,12 @@ import numpy as np
 F32 = np.float32
 VARIABLES = []          # every Variable created since the last reset_registry()
 
+# WIDE: run the whole graph in float64 -- constants and inputs are still rounded to float32 first
+# (the model keeps the reference's fp32 parameters), only the ARITHMETIC is carried out in double.
+# |reference(fp32) - reference(WIDE)| is the reference's own total fp32 rounding error: the level
+# below which agreement between two different fp32 implementations of it cannot be demanded.
+WIDE = False
+
 
 def reset_registry():
     del VARIABLES[:]
@@ -43,10 +49,12 @@ def _coerce(x):
     if isinstance(x, (bool, np.bool_)):
         return x
     if isinstance(x, (int, float, np.integer, np.floating)):
-        return F32(x)
+        return np.float64(F32(x)) if WIDE else F32(x)
     a = np.asarray(x)
-    if a.dtype == np.float64:
+    if a.dtype == np.float64 and not WIDE:
         return a.astype(F32)
+    if WIDE and a.dtype == np.float32:
+        return a.astype(np.float64)
     return a
 
 
@@ -106,6 +114,8 @@ class Variable(Node):
     def __init__(self, initial_value, name=None, dtype=None):
         Node.__init__(self, None, [])
         self.init = np.array(initial_value)
+        if WIDE and self.init.dtype == np.float32:
+            self.init = self.init.astype(np.float64)
         self.val = self.init.copy()
         self.name = name
         VARIABLES.append(self)
@@ -178,7 +188,7 @@ def constant(v, dtype=None, name=None):
     a = np.asarray(v)
     if a.dtype == np.float64:
         a = a.astype(F32)
-    return Node(lambda: a, [])
+    return Node(lambda: _coerce(a), [])
 
 
 # ALT_LIBM: evaluate the transcendental functions in float64 and round once to float32, i.e. run
@@ -241,7 +251,7 @@ def where(cond, x, y, name=None):
 
 
 def clip_by_value(x, lo, hi, name=None):
-    return Node(lambda a: np.minimum(np.maximum(_coerce(a), F32(lo)), F32(hi)), [x])
+    return Node(lambda a: np.minimum(np.maximum(_coerce(a), _coerce(lo)), _coerce(hi)), [x])
 
 
 def pad(x, paddings, mode='CONSTANT', name=None):

@@ -50,4 +50,4 @@ class CudaModel:
         self.m.close()
 
 
-from oracle.monodomain_np import rel_err, var_scale  # noqa: E402,F401  (re-exported)
+from oracle.monodomain_np import rel_err, var_floor  # noqa: E402,F401  (re-exported)

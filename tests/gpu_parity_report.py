@@ -8,7 +8,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from conftest import golden_names, load_fixture  # noqa: E402
-from cuda_adapter import CudaModel, rel_err, var_scale  # noqa: E402
+from cuda_adapter import CudaModel, rel_err, var_floor  # noqa: E402
 from oracle import monodomain_np as onp  # noqa: E402
 
 
@@ -22,7 +22,7 @@ def main():
             for v in meta['vars']:
                 ref = arr['s%d__%s' % (i, v)]
                 got = m.state[v]
-                rows.append((rel_err(got, ref, var_scale(meta['model'], v)), i, v,
+                rows.append((rel_err(got, ref, var_floor(meta['model'], v)), i, v,
                              float(np.nanmax(np.abs(got - ref)))))
 
         m, trace = onp.run_fixture(meta, check, model_factory=CudaModel)

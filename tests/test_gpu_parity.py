@@ -4,12 +4,17 @@
   (3) size-independent properties at the full benchmark sizes.
 
 Tolerance (written here, used everywhere below): for every state variable and snapshot,
-    rel_err = max |cuda - ref| / max(|ref|, 1e-3 * range(var))  <=  max(1e-5, 3 * noise)
-where `noise` is the reference's own deviation from itself when ONLY its fp32 math library is
-swapped for another correctly-rounding one (recorded per plane in the fixture, see
-oracle/make_golden.py / oracle/tfshim.ALT_LIBM).  1e-5 is BASELINE.json's per-step bar; the noise
-term exists because near the removable singularities of the BR / Courtemanche rate functions the
-reference's fp32 result is itself only defined to ~1e-4 (it is never looser than 3x that)."""
+    rel_err = max |cuda - ref| / max(|ref|, floor(var))  <=  max(1e-5, 3 * noise)
+(floor: 0.1 % of the variable's range; the full range for the accumulating voltage V of BR /
+Courtemanche -- see oracle.monodomain_np.var_floor)
+where `noise` = max(the reference's deviation from itself when ONLY its fp32 math library is
+swapped for another correctly-rounding one, the reference's total fp32 rounding error against the
+same graph evaluated in float64), both recorded per plane in the fixture (oracle/make_golden.py,
+oracle/tfshim.ALT_LIBM / WIDE).  1e-5 is BASELINE.json's per-step bar and it is what 4v and the
+exact-gate BR are held to; the noise term exists because the reference's OWN fp32 result is only
+defined to ~1e-4 for the degree-8 polynomial gates (ill-conditioned scaled-monomial basis) and for
+the Courtemanche u/v gates (a 1e-15-wide sigmoid): no second fp32 implementation can agree with it
+more closely than it agrees with exact arithmetic.  Never looser than 3x that."""
 import numpy as np
 import pytest
 
@@ -36,7 +41,7 @@ def test_per_step_parity_with_reference_fixture(cuda, name):
     def check(i, m):
         for v in meta['vars']:
             key = 's%d__%s' % (i, v)
-            e = onp.rel_err(m.state[v], arr[key], onp.var_scale(meta['model'], v))
+            e = onp.rel_err(m.state[v], arr[key], onp.var_floor(meta['model'], v))
             tol = onp.parity_tolerance(meta, key)
             assert e <= tol, '%s %s: rel_err %.3e > tol %.3e' % (name, key, e, tol)
         seen.append(i)
@@ -83,7 +88,7 @@ def model_noise(kind):
     for n in SHORT:
         meta, _ = load_fixture(n)
         if meta['model'] == kind:
-            worst = max([worst] + list(meta['noise'].values()))
+            worst = max([worst] + list(meta['noise'].values()) + list(meta['rounding'].values()))
     return worst
 
 
@@ -116,7 +121,7 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
             if i == iters // 2:
                 m.fire('s2')
     for v in ref.state:
-        e = onp.rel_err(gpu.state[v], ref.state[v], onp.var_scale(kind, v))
+        e = onp.rel_err(gpu.state[v], ref.state[v], onp.var_floor(kind, v))
         assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (kind, v, e, tol)
     gpu.close()
 
@@ -201,7 +206,7 @@ def test_planar_wave_property_at_4096(cuda):
     for v in ('U', 'V', 'W', 'S'):
         a = gpu.state[v]
         assert np.array_equal(a, np.broadcast_to(a[0], a.shape)), 'rows differ for %s' % v
-        assert onp.rel_err(a[:5], ref.state[v], 1.0) <= 1e-5
+        assert onp.rel_err(a[:5], ref.state[v], 1e-3) <= 1e-5
     gpu.close()
 
 
@@ -235,5 +240,5 @@ def test_empty_and_edge_geometries(cuda):
         gpu.m._ctx.stimulate('U', 0, 0, 0, 0, 1.0, 0.0)
         ref.state['U'] = np.maximum(ref.state['U'], np.float32(0.0))
         for v in ('U', 'V', 'W', 'S'):
-            assert onp.rel_err(gpu.state[v], ref.state[v], 1.0) <= 1e-5, (H, W, v)
+            assert onp.rel_err(gpu.state[v], ref.state[v], 1e-3) <= 1e-5, (H, W, v)
         gpu.close()
