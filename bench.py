@@ -329,7 +329,9 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'of measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = FALLBACK_HBM, 'of fallback (B200_PROFILING.md)'
-    launch_ms = ms_dev / max(launches_rank, 1)
+    # one time step of this rank's shard = one step kernel (three launches when sharded: the two
+    # boundary rows first, then the interior, so that the halo exchange overlaps the interior)
+    launch_ms = ms_dev / (K * 10)
     achieved = B_ALG * rows * size / (launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -340,7 +342,8 @@ def main():
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'kernel': 'fib::step_kernel<Fenton4v,...>', 'bytes_per_cell_step': B_ALG,
-                'avg_launch_ms': launch_ms, 'cells_per_launch': rows * size}
+                'avg_launch_ms': launch_ms, 'cells_per_launch': rows * size,
+                'launches_per_time_step': launches_rank / (K * 10.0)}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': K, 'warmup': Wm,

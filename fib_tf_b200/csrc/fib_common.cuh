@@ -44,7 +44,7 @@ template <> struct VecIO<4> {
 // tf.clip_by_value(x, lo, hi) == min(max(x, lo), hi) with NaN propagating (ionic.py:122-123,
 // br.py:167-168).  fminf/fmaxf would swallow a NaN; the reference does not.
 __device__ __forceinline__ float clip_nan(float x, float lo, float hi) {
-  return x < lo ? lo : (x > hi ? hi : x);
+  return min_nan(max_nan(x, lo), hi);
 }
 
 // IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).

@@ -146,23 +146,19 @@ struct BeelerReuter {
     const float k53 = k * E53;
     const float d23 = V0 + 23.0f;
     // (V0+23) / (1 - e^{-0.04 (V0+23)}): removable singularity at -23 mV.  Away from it
-    // 1 - e^{-0.92}/k is accurate and free (k is already known); within +-6 mV the expm1
-    // polynomial takes over (warp-uniform branch, rarely taken).
+    // 1 - e^{-0.92}/k is accurate and free (k is already known); within +-3 mV the expm1
+    // polynomial takes over.
     constexpr float E23N = 0.3985190410845142f;   // e^{-0.04*23}
     float one_m_e = fmaf(-E23N, m_rcp(k), 1.0f);
     {
-      const float z = -0.04f * d23;
-      const bool near = fabsf(z) < 0.25f;
-      if (__any_sync(__activemask(), near)) {
-        float q = 1.98412698412698e-4f;
-        q = fmaf(q, z, 1.38888888888889e-3f);
-        q = fmaf(q, z, 8.33333333333333e-3f);
-        q = fmaf(q, z, 4.16666666666667e-2f);
-        q = fmaf(q, z, 1.66666666666667e-1f);
-        q = fmaf(q, z, 0.5f);
-        q = fmaf(q * z, z, z);                    // expm1(z)
-        one_m_e = near ? -q : one_m_e;
-      }
+      const float z = -0.04f * d23;               // |z| < 0.125 <=> within 3.1 mV of the singularity
+      float q = 1.38888888888889e-3f;
+      q = fmaf(q, z, 8.33333333333333e-3f);
+      q = fmaf(q, z, 4.16666666666667e-2f);
+      q = fmaf(q, z, 1.66666666666667e-1f);
+      q = fmaf(q, z, 0.5f);
+      q = fmaf(q * z, z, z);                      // expm1(z)
+      one_m_e = fabsf(z) < 0.125f ? -q : one_m_e;
     }
     const float sing = m_div(d23, one_m_e);
     const float iK1 = 0.35f * (m_div(4.f * fmaf(k, E85, -1.f), fmaf(k53, k53, k53)) + 0.2f * sing);

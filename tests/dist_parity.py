@@ -1,0 +1,65 @@
+"""torchrun --nproc-per-node N tests/dist_parity.py : on N GPUs, the NCCL row-sharded run (one
+process per GPU, halo rows over ncclSend/ncclRecv) must be BIT-IDENTICAL to the unsharded run
+that rank 0 performs on its own GPU.  All three model families, with a phase field and a
+stimulus that straddles the seams."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    from cuda_adapter import CLASSES
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    base = {'width': 200, 'height': 131, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.1, 'duration': 1,
+            'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False,
+            'cheby': False, 'ultra_slow': False}
+    ok = True
+    for kind, extra, iters in (('fenton4v', {}, 4), ('br', {'cheby': True, 'skip': True}, 5),
+                               ('court', {}, 12), ('court_ultra', {'ultra_slow': True}, 8)):
+        cfg = dict(base, **extra)
+        models = [CLASSES[kind](dict(cfg, distributed=True, device=local))]
+        if rank == 0:
+            models.append(CLASSES[kind](dict(cfg, device=local)))
+        for m in models:
+            m.add_hole_to_phase_field(90, 60, 17)
+            m.define()
+            m.add_pace_op('s2', 'luq', float(m.max_v) * 0.4)
+        for i in range(iters):
+            for m in models:
+                m._ctx.step(0, 1)
+                if kind == 'court' and i % 5 == 0:
+                    m.fire_op('slow')
+                if i == 1:
+                    m.fire_op('s2')
+        for name in models[0]._ctx.var_names:
+            full = models[0]._State[name].eval()          # gathered over ranks (collective)
+            if rank == 0:
+                ref = models[1]._State[name].eval()
+                same = np.array_equal(full, ref)
+                ok &= same
+                if not same:
+                    print('MISMATCH %s %s max|d|=%g' % (kind, name, np.abs(full - ref).max()))
+        if rank == 0:
+            print('%-12s %d ranks: sharded == unsharded: %s' % (kind, world, ok), flush=True)
+        for m in models:
+            m.close()
+    flag = torch.tensor([1 if ok else 0], device='cuda')
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    if not flag.item():
+        sys.exit(1)
+    if rank == 0:
+        print('DIST PARITY OK')
+
+
+if __name__ == '__main__':
+    main()
