@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('FIB_B200_LIB') or os.path.join(_HERE, 'libfibb200.so'
 # model ids / flags / ops / tables: keep in sync with include/fib_b200.h
 FENTON4V, BR, COURT, COURT_ULTRA = 0, 1, 2, 3
 F_CHEBY, F_SKIP, F_LUT, F_ULTRA_SLOW, F_NO_CHRONIC, F_NO_GRAPH = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+F_NO_CLIP = 0x40
 OP_ODE, OP_SLOW = 0, 1
 TABLE_BR_CHEBY, TABLE_COURT_LUT = 0, 1
 ABI_VERSION = 1

@@ -518,6 +518,9 @@ static cudaError_t launch_court(fib_ctx* c, int lr0, int nrows) {
   a.p.ddt = (float)(c->cfg.diff * dt);
   a.p.e_fCa = (float)expm1((double)(float)(-dts / 2.0));
   a.p.e_u = (float)expm1((double)(float)(-dts / 8.0));
+  const bool noclip = c->cfg.flags & FIB_F_NO_CLIP;
+  a.p.clip_lo = noclip ? -INFINITY : 0.00001f;
+  a.p.clip_hi = noclip ? INFINITY : 0.99999f;
   a.p.k_to = (float)((1.0 - 0.5 * chron) * 100 * 0.1652);
   a.p.k_Kur = (float)((1.0 - 0.5 * chron) * 100);
   a.p.k_CaL = (float)((1.0 - 0.7 * chron) * 100 * 0.12375);

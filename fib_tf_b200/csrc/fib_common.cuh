@@ -53,10 +53,15 @@ __device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, fl
   float e = m_expm1(m_div(neg_dt, tau));
   return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
-// gates whose dt/tau is small except in rare cells (everything but the fast sodium activation)
-__device__ __forceinline__ float rush_larsen_slow(float g, float g_inf, float tau, float neg_dt) {
-  float e = m_expm1_small(m_div(neg_dt, tau));
-  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+// Rush-Larsen with caller-supplied clip bounds: (1e-5, 0.99999) for the Python models, (-inf, +inf)
+// for the native courtemanche.h rule, which does not clip (courtemanche.h:287-292)
+__device__ __forceinline__ float rush_larsen_b(float g, float g_inf, float tau, float neg_dt, float lo,
+                                               float hi) {
+  float e = m_expm1(m_div(neg_dt, tau));
+  return clip_nan(fmaf(g - g_inf, e, g), lo, hi);
+}
+__device__ __forceinline__ float rush_larsen_eb(float g, float g_inf, float e, float lo, float hi) {
+  return clip_nan(fmaf(g - g_inf, e, g), lo, hi);
 }
 // same with e = expm1(-dt/tau) precomputed (Python-scalar tau: court.py:189,243)
 __device__ __forceinline__ float rush_larsen_e(float g, float g_inf, float e) {

@@ -42,7 +42,6 @@ __device__ __forceinline__ float m_rcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float m_div(float a, float b) { return a / b; }
 __device__ __forceinline__ float m_exp(float x) { return expf(x); }
 __device__ __forceinline__ float m_expm1(float x) { return expm1f(x); }
-__device__ __forceinline__ float m_expm1_small(float x) { return expm1f(x); }
 __device__ __forceinline__ float m_log(float x) { return logf(x); }
 __device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
 // 1 / (1 + e^{-2z}) == 0.5 (1 + tanh z)
@@ -76,7 +75,6 @@ __device__ __forceinline__ float m_expm1(float x) {
   const float e = m_exp(x) - 1.0f;
   return fabsf(x) < 0.125f ? p : e;
 }
-__device__ __forceinline__ float m_expm1_small(float x) { return m_expm1(x); }
 
 __device__ __forceinline__ float m_log(float x) { return sfu_lg2(x) * 0.693147182464599609375f; }
 __device__ __forceinline__ float m_sqrt(float x) { return sfu_sqrt(x); }

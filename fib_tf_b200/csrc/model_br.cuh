@@ -69,10 +69,6 @@ __device__ __forceinline__ void br_inf_rate_exact(float v, float& inf, float& ra
 __device__ __forceinline__ float rush_larsen_rate(float g, float g_inf, float rate, float neg_dt) {
   return rush_larsen_e(g, g_inf, m_expm1(neg_dt * rate));
 }
-__device__ __forceinline__ float rush_larsen_rate_slow(float g, float g_inf, float rate, float neg_dt) {
-  return rush_larsen_e(g, g_inf, m_expm1_small(neg_dt * rate));
-}
-
 // Horner evaluation of c0 + c1 x + ... + c8 x^8.  Every FMA has exactly ONE constant-bank operand
 // (the coefficient lives in the kernel parameter bank), so no LDC is needed; Estrin's scheme was
 // measured slower because its two-constant FMAs saturate the ADU pipe with constant loads.  The
@@ -116,24 +112,24 @@ struct BeelerReuter {
       const float x = (V0 + 30.0f) * (1.0f / 60.0f);
 #define FIB_BR_GATE(RL, g, idx, ndt) \
   s[idx] = RL(s[idx], br_poly8(p.poly[2 * (g)], x), br_poly8(p.poly[2 * (g) + 1], x), ndt)
-      FIB_BR_GATE(rush_larsen, 1, 1, p.neg_dt);                 // m: dt/tau_m is O(1..10)
-      FIB_BR_GATE(rush_larsen_slow, 2, 2, p.neg_dt);            // h
+      FIB_BR_GATE(rush_larsen, 1, 1, p.neg_dt);                 // m
+      FIB_BR_GATE(rush_larsen, 2, 2, p.neg_dt);                 // h
       if (SLOW) {
-        FIB_BR_GATE(rush_larsen_slow, 0, 6, p.neg_dt_slow);     // xi
-        FIB_BR_GATE(rush_larsen_slow, 3, 3, p.neg_dt_slow);     // j
-        FIB_BR_GATE(rush_larsen_slow, 4, 4, p.neg_dt_slow);     // d
-        FIB_BR_GATE(rush_larsen_slow, 5, 5, p.neg_dt_slow);     // f
+        FIB_BR_GATE(rush_larsen, 0, 6, p.neg_dt_slow);         // xi
+        FIB_BR_GATE(rush_larsen, 3, 3, p.neg_dt_slow);         // j
+        FIB_BR_GATE(rush_larsen, 4, 4, p.neg_dt_slow);         // d
+        FIB_BR_GATE(rush_larsen, 5, 5, p.neg_dt_slow);         // f
       }
 #undef FIB_BR_GATE
     } else {
       float inf, rate;
       br_inf_rate_exact<1>(V0, inf, rate); s[1] = rush_larsen_rate(M, inf, rate, p.neg_dt);
-      br_inf_rate_exact<2>(V0, inf, rate); s[2] = rush_larsen_rate_slow(H, inf, rate, p.neg_dt);
+      br_inf_rate_exact<2>(V0, inf, rate); s[2] = rush_larsen_rate(H, inf, rate, p.neg_dt);
       if (SLOW) {
-        br_inf_rate_exact<0>(V0, inf, rate); s[6] = rush_larsen_rate_slow(XI, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<3>(V0, inf, rate); s[3] = rush_larsen_rate_slow(J, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<4>(V0, inf, rate); s[4] = rush_larsen_rate_slow(D, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<5>(V0, inf, rate); s[5] = rush_larsen_rate_slow(F, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<0>(V0, inf, rate); s[6] = rush_larsen_rate(XI, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<3>(V0, inf, rate); s[3] = rush_larsen_rate(J, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<4>(V0, inf, rate); s[4] = rush_larsen_rate(D, inf, rate, p.neg_dt_slow);
+        br_inf_rate_exact<5>(V0, inf, rate); s[5] = rush_larsen_rate(F, inf, rate, p.neg_dt_slow);
       }
     }
 

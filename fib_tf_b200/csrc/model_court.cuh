@@ -205,6 +205,7 @@ struct Courtemanche {
     float ddt;                    // fp32(diff * dt_fast)        (court.py:229)
     float e_fCa;                  // expm1(fp32(-dt_x / 2.0)), Python-scalar tau (court.py:189)
     float e_u;                    // expm1(fp32(-dt_x / 8.0))                    (court.py:243)
+    float clip_lo, clip_hi;       // gate clip: (1e-5, 0.99999) (ionic.py:122-123) or (-inf, +inf)
     float k_to, k_Kur, k_CaL;     // (1-0.5c)*Cm*g_to, (1-0.5c)*Cm, (1-0.7c)*Cm*g_Ca_L folded in double
                                   // on the host like the reference's Python (court.py:193-194,218)
   };
@@ -242,24 +243,24 @@ struct Courtemanche {
                 u = s[S_u], v = s[S_v], w = s[S_w];
 
     // gates (court.py:175-189); _w_ is clocked with the step of '_d_' (court.py:177) = slow
-    s[S_d] = rush_larsen_slow(d, q[Q_d_inf], q[Q_tau_d], nds);
-    s[S_f] = rush_larsen_slow(f, q[Q_f_inf], q[Q_tau_f], nds);
-    s[S_w] = rush_larsen_slow(w, q[Q_w_inf], q[Q_tau_w], nds);
-    s[S_m] = rush_larsen(m, q[Q_m_inf], q[Q_tau_m], ndf);
-    s[S_h] = rush_larsen_slow(h, q[Q_h_inf], q[Q_tau_h], ndf);
-    s[S_j] = rush_larsen_slow(j, q[Q_j_inf], q[Q_tau_j], nds);
-    s[S_oa] = rush_larsen_slow(oa, q[Q_oa_inf], q[Q_tau_oa], nds);
-    s[S_oi] = rush_larsen_slow(oi, q[Q_oi_inf], q[Q_tau_oi], nds);
-    s[S_ua] = rush_larsen_slow(ua, q[Q_ua_inf], q[Q_tau_ua], nds);
-    s[S_ui] = rush_larsen_slow(ui, q[Q_ui_inf], q[Q_tau_ui], nds);
-    s[S_xr] = rush_larsen_slow(xr, q[Q_xr_inf], q[Q_tau_xr], nds);
-    s[S_xs] = rush_larsen_slow(xs, q[Q_xs_inf], q[Q_tau_xs], nds);
+    s[S_d] = rush_larsen_b(d, q[Q_d_inf], q[Q_tau_d], nds, p.clip_lo, p.clip_hi);
+    s[S_f] = rush_larsen_b(f, q[Q_f_inf], q[Q_tau_f], nds, p.clip_lo, p.clip_hi);
+    s[S_w] = rush_larsen_b(w, q[Q_w_inf], q[Q_tau_w], nds, p.clip_lo, p.clip_hi);
+    s[S_m] = rush_larsen_b(m, q[Q_m_inf], q[Q_tau_m], ndf, p.clip_lo, p.clip_hi);
+    s[S_h] = rush_larsen_b(h, q[Q_h_inf], q[Q_tau_h], ndf, p.clip_lo, p.clip_hi);
+    s[S_j] = rush_larsen_b(j, q[Q_j_inf], q[Q_tau_j], nds, p.clip_lo, p.clip_hi);
+    s[S_oa] = rush_larsen_b(oa, q[Q_oa_inf], q[Q_tau_oa], nds, p.clip_lo, p.clip_hi);
+    s[S_oi] = rush_larsen_b(oi, q[Q_oi_inf], q[Q_tau_oi], nds, p.clip_lo, p.clip_hi);
+    s[S_ua] = rush_larsen_b(ua, q[Q_ua_inf], q[Q_tau_ua], nds, p.clip_lo, p.clip_hi);
+    s[S_ui] = rush_larsen_b(ui, q[Q_ui_inf], q[Q_tau_ui], nds, p.clip_lo, p.clip_hi);
+    s[S_xr] = rush_larsen_b(xr, q[Q_xr_inf], q[Q_tau_xr], nds, p.clip_lo, p.clip_hi);
+    s[S_xs] = rush_larsen_b(xs, q[Q_xs_inf], q[Q_tau_xs], nds, p.clip_lo, p.clip_hi);
     const float f_Ca_inf = m_rcp(1.0f + Ca_i * FIB_RCPF(0.00035));
-    s[S_f_Ca] = rush_larsen_e(f_Ca, f_Ca_inf, p.e_fCa);
+    s[S_f_Ca] = rush_larsen_eb(f_Ca, f_Ca_inf, p.e_fCa, p.clip_lo, p.clip_hi);
     float us = 1.f;
     if (US) {
       us = s[S_us];
-      s[S_us] = rush_larsen_slow(us, q[Q_us_inf], q[Q_tau_us], nds);   // court_ultra.py:198-199
+      s[S_us] = rush_larsen_b(us, q[Q_us_inf], q[Q_tau_us], nds, p.clip_lo, p.clip_hi);   // court_ultra.py:198-199
     }
 
     // currents (court.py:191-221)
@@ -304,10 +305,10 @@ struct Courtemanche {
     const float Fn = 1000.0f * ((float)(1.0e-15 * V_rel) * i_rel -
                                 (float)(1.0e-15 / (2.0 * F)) * (0.5f * i_Ca_L - 0.2f * i_NaCa));
     const float u_inf = m_rcp(1.0f + m_exp(-(Fn - 3.4175e-13f) * FIB_RCPF(1.367e-15)));
-    s[S_u] = rush_larsen_e(u, u_inf, p.e_u);
+    s[S_u] = rush_larsen_eb(u, u_inf, p.e_u, p.clip_lo, p.clip_hi);
     const float tau_v = 1.91f + 2.09f * u_inf;
     const float v_inf = 1.0f - m_rcp(1.0f + m_exp(-(Fn - 6.835e-14f) * FIB_RCPF(1.367e-15)));
-    s[S_v] = rush_larsen(v, v_inf, tau_v, nds);
+    s[S_v] = rush_larsen_b(v, v_inf, tau_v, nds, p.clip_lo, p.clip_hi);
     const float i_up = (float)I_up_max * m_rcp(1.0f + m_div((float)K_up, Ca_i));
     const float i_up_leak = ((float)I_up_max * Ca_up) * FIB_RCPF(Ca_up_max);
     s[S_Ca_up] = fmaf(i_up - (i_up_leak + (i_tr * (float)V_rel) * FIB_RCPF(V_up)), dts, Ca_up);

@@ -57,6 +57,8 @@ typedef enum {
 #define FIB_F_ULTRA_SLOW 0x08u  /* court_ultra.py:81-82,198-199,221-222: 22nd state '_us_'         */
 #define FIB_F_NO_CHRONIC 0x10u  /* Courtemanche: chronic-AF remodelling OFF (court.py:41 sets it ON) */
 #define FIB_F_NO_GRAPH   0x20u  /* launch kernels directly instead of replaying a CUDA graph         */
+#define FIB_F_NO_CLIP    0x40u  /* Courtemanche: no [1e-5, 0.99999] clip of the Rush-Larsen gates, as in
+                                   the native integrate_gate (courtemanche.h:287-292); court.py clips   */
 
 typedef struct {
   uint32_t struct_size;      /* = sizeof(fib_config), for ABI evolution                              */

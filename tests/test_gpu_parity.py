@@ -242,3 +242,77 @@ def test_empty_and_edge_geometries(cuda):
         for v in ('U', 'V', 'W', 'S'):
             assert onp.rel_err(gpu.state[v], ref.state[v], 1e-3) <= 1e-5, (H, W, v)
         gpu.close()
+
+
+def test_lut_path_against_the_compiled_reference_header(cuda):
+    """courtemanche.h compiled on the host (oracle/_ref): deriv<Courtemanche> with its 150x30 table
+    and forward Euler state += dt*rate, against the CUDA LUT flavour with the
+    SAME table uploaded, the native no-clip gate rule and diff = 0 (every cell an independent ODE).
+
+    (1) ONE step from 150 x 8 different states: every table row (voltages at half-integers, safely
+        inside a row of the truncating lookup) x 8 perturbations of the gates / concentrations.
+        Bar: |new_cuda - new_ref| <= 1e-5 * max(|increment|, 1e-3 * floor) + 1 ulp(state).
+    (2) 30 steps from the same states: the lookup is discontinuous in V, so a 1-ulp difference just
+        below an integer voltage reads another table row; bar 1e-3 in the rel_err metric."""
+    from fib_tf_b200 import _capi
+    from oracle import cpu_port
+    ref = cpu_port.court_ref()
+    if ref is None:
+        pytest.skip('oracle/_ref was not built')
+    table = np.zeros([150, 30], np.float32)
+    ref.ref_init_table(table)
+    HI, WI, dt = 150, 8, 0.1
+    cell0 = np.zeros(21, np.float32)
+    ref.ref_init_cell(cell0, 0)
+    init = np.zeros([HI, WI, 21], np.float32)
+    for r in range(HI):
+        for c in range(WI):
+            st = cell0.copy()
+            f = np.float32(0.55 + 0.13 * c)
+            st[1:] = st[1:] * f
+            gates = [2, 3, 4, 6, 7, 8, 9, 10, 11, 13, 14, 15, 17, 18, 19]      # enum States
+            st[gates] = np.clip(st[gates], 1e-4, 0.9999)
+            st[0] = r - 100 + 0.5
+            init[r, c] = st
+    # one ring of SYMMETRIC padding around the 150 x 8 experiment, so that the kernel's
+    # enforce_boundary (border ring := neighbouring interior cell) changes nothing
+    init = np.pad(init, ((1, 1), (1, 1), (0, 0)), mode='symmetric')
+    H, W = init.shape[:2]
+
+    def cuda_run(steps):
+        ctx = _capi.Context(_capi.COURT_ULTRA, H, W, dt, 0.0, flags=_capi.F_LUT | _capi.F_NO_CLIP)
+        ctx.set_table(_capi.TABLE_COURT_LUT, table)
+        for k, name in enumerate(ctx.var_names):
+            ctx.set_state(name, init[:, :, k])
+        ctx.step(_capi.OP_ODE, steps)
+        out = np.stack([ctx.get_state(n) for n in ctx.var_names], axis=2)
+        names = list(ctx.var_names)
+        ctx.close()
+        return out, names
+
+    def ref_run(steps):
+        out = init.copy()
+        rate = np.zeros(21, np.float32)
+        inc = np.zeros_like(out)
+        for r in range(H):
+            for c in range(W):
+                st = out[r, c].copy()
+                for _ in range(steps):
+                    ref.ref_deriv(st, rate, dt, table, 1)
+                    inc[r, c] = np.float32(dt) * rate
+                    st = (st + np.float32(dt) * rate).astype(np.float32)
+                out[r, c] = st
+        return out, inc
+
+    got, names = cuda_run(1)
+    want, inc = ref_run(1)
+    for k, name in enumerate(names):
+        fl = onp.var_floor('court_ultra', name)
+        tol = 1e-5 * np.maximum(np.abs(inc[:, :, k]), 1e-3 * fl) + np.spacing(np.abs(want[:, :, k]))
+        bad = np.abs(got[:, :, k].astype(np.float64) - want[:, :, k]) > tol
+        assert not bad.any(), (name, int(bad.sum()), float(np.abs(got[:, :, k] - want[:, :, k]).max()))
+    got, names = cuda_run(30)
+    want, _ = ref_run(30)
+    for k, name in enumerate(names):
+        e = onp.rel_err(got[:, :, k], want[:, :, k], onp.var_floor('court_ultra', name))
+        assert e <= 1e-3, (name, e)
