@@ -113,6 +113,8 @@ struct fib_ctx {
   int cur = 0;
   float* s[S_COUNT] = {nullptr};      // other planes
   float* phase = nullptr;             // halo layout
+  unsigned char* pmask = nullptr;     // [rows][pmask_pitch] non-trivial-phase flags per 32 columns
+  int pmask_pitch = 0;
   float* lut = nullptr;               // 150 x 30, the ABI layout (courtemanche.h order)
   float* lut_t = nullptr;             // 30 x 160 transposed copy the kernels read
   bool have_lut = false, have_cheb = false, halo_dirty = true, comm_pending = false;
@@ -143,13 +145,34 @@ struct DevGuard {
 __global__ void stim_kernel(float* __restrict__ x, Geom g, int halo, int r0, int r1, int c0, int c1,
                             float value, float floor_v) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lr = blockIdx.y;
-  if (c >= g.W || lr >= g.rows) return;
-  const int gr = g.row0 + lr;
-  const float m = (gr >= r0 && gr < r1 && c >= c0 && c < c1) ? value : floor_v;
-  float* p = x + (size_t)(lr + halo) * g.pitch + c;
-  const float v = *p;
-  *p = m > v ? m : v;
+  if (c >= g.W) return;
+  for (int lr = blockIdx.y; lr < g.rows; lr += gridDim.y) {
+    const int gr = g.row0 + lr;
+    const float m = (gr >= r0 && gr < r1 && c >= c0 && c < c1) ? value : floor_v;
+    float* p = x + (size_t)(lr + halo) * g.pitch + c;
+    const float v = *p;
+    *p = m > v ? m : v;
+  }
+}
+
+// fib_set_phase: flag the 32-column blocks of each row whose phase term can be non-zero, i.e.
+// where phi is not constant over rows r-1..r+1 (REFLECT) x columns c0-1..c0+32 (clipped: the
+// reflected columns -1 -> 1 and W -> W-2 lie inside that range).
+__global__ void phase_mask_kernel(const float* __restrict__ phase, Geom g, unsigned char* __restrict__ mask,
+                                  int mpitch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= mpitch) return;
+  const int c0 = max(b * 32 - 1, 0), c1 = min(b * 32 + 32, g.W - 1);
+  for (int lr = blockIdx.y; lr < g.rows; lr += gridDim.y) {
+    const int gr = g.row0 + lr;
+    const float first = phase[(size_t)(lr + 1) * g.pitch + c0];
+    bool same = true;
+    for (int dr = -1; dr <= 1; ++dr) {
+      const int rr = reflecti(gr + dr, g.H) - g.row0 + 1;
+      for (int c = c0; c <= c1; ++c) same &= (phase[(size_t)rr * g.pitch + c] == first);
+    }
+    mask[(size_t)lr * mpitch + b] = same ? 0 : 1;
+  }
 }
 
 __global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict__ w, Geom g,
@@ -297,6 +320,7 @@ extern "C" int fib_destroy(fib_ctx* c) {
   for (int b = 0; b < 2; ++b) cudaFree(c->x[b]);
   for (int k = 0; k < S_COUNT; ++k) cudaFree(c->s[k]);
   cudaFree(c->phase);
+  cudaFree(c->pmask);
   cudaFree(c->lut);
   cudaFree(c->lut_t);
   cudaFree(c->red);
@@ -388,7 +412,9 @@ extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, 
   c->graphs.clear();
   if (!rows_host) {
     CU(cudaFree(c->phase));
+    CU(cudaFree(c->pmask));
     c->phase = nullptr;
+    c->pmask = nullptr;
     return 0;
   }
   const int need0 = max(c->g.row0 - 1, 0), need1 = min(c->g.row0 + c->g.rows + 1, c->g.H);
@@ -404,6 +430,14 @@ extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, 
                        c->g.pitch * sizeof(float),
                        rows_host + (size_t)(need0 - first_row) * c->g.W, c->g.W * sizeof(float),
                        c->g.W * sizeof(float), need1 - need0, cudaMemcpyHostToDevice, c->stream));
+  c->pmask_pitch = (c->g.W + 31) / 32;
+  if (!c->pmask) CU(cudaMalloc(&c->pmask, (size_t)c->g.rows * c->pmask_pitch));
+  {
+    dim3 block(64), grid((c->pmask_pitch + 63) / 64, min(c->g.rows, 65535));
+    phase_mask_kernel<<<grid, block, 0, c->stream>>>(c->phase, c->g, c->pmask, c->pmask_pitch);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -498,6 +532,8 @@ static void fill_common(fib_ctx* c, StepArgs<M>& a, int lr0, int nrows) {
   a.xout = c->x[c->cur ^ 1];
   for (int k = 0; k < M::NS; ++k) a.s[k] = c->s[k];
   a.phase = c->phase;
+  a.pmask = c->pmask;
+  a.pmask_pitch = c->pmask_pitch;
   a.lut = c->lut_t;
   a.lr0 = lr0;
   a.nrows = nrows;
@@ -791,7 +827,7 @@ extern "C" int fib_stimulate(fib_ctx* c, int var, int r0, int r1, int c0, int c1
     CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     c->comm_pending = false;
   }
-  dim3 block(128), grid((c->g.W + 127) / 128, c->g.rows);
+  dim3 block(128), grid((c->g.W + 127) / 128, min(c->g.rows, 65535));
   float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
   stim_kernel<<<grid, block, 0, c->stream>>>(base, c->g, var == 0 ? 1 : 0, r0, r1, c0, c1, value, floor_v);
   CU(cudaGetLastError());

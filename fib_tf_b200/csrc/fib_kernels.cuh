@@ -32,6 +32,8 @@ struct StepArgs {
   float* xout;                   // ping-pong target (halo layout)
   float* s[M::NS > 0 ? M::NS : 1];  // non-diffusing planes (in place)
   const float* phase;            // halo layout, or nullptr
+  const unsigned char* pmask;    // [rows][pmask_pitch]: 1 where the phase term of a 32-column block
+  int pmask_pitch;               //   can be non-zero (fib_set_phase), 0 where phi is locally constant
   const float* lut;              // Courtemanche table, transposed [30][160] (global), or nullptr
   int lr0, nrows;                // local row range [lr0, lr0+nrows) processed by this launch
   typename M::Params p;
@@ -58,14 +60,7 @@ step_kernel(const Geom g, const StepArgs<M> a) {
   auto prow = [&](int gr) { return (reflecti(gr, g.H) - g.row0 + 1) * pitch; };
 
   float xN[VEC + 2], xC[VEC + 2], xS[VEC + 2];
-  float pN[VEC + 2], pC[VEC + 2], pS[VEC + 2];   // phase-field window (REFLECT padding)
-  if (M::NEED_LAP) {
-    load_enforced_row<VEC>(a.xin, xrow(gr0 - 1), cw, g.W, xN);
-    if (PHASE) {
-      load_reflect_row<VEC>(a.phase, prow(gr0 - 1), cw, g.W, pN);
-      load_reflect_row<VEC>(a.phase, prow(gr0), cw, g.W, pC);
-    }
-  }
+  if (M::NEED_LAP) load_enforced_row<VEC>(a.xin, xrow(gr0 - 1), cw, g.W, xN);
   load_enforced_row<VEC>(a.xin, xrow(gr0), cw, g.W, xC);
 
   int off = (gr0 - g.row0) * pitch + c;          // my cell in a non-halo plane; += pitch per row
@@ -73,9 +68,19 @@ step_kernel(const Geom g, const StepArgs<M> a) {
   for (int i = 0; i < R; ++i, off += pitch) {
     const int gr = gr0 + i;
     if (gr < gend) {
-      if (M::NEED_LAP) {
-        load_enforced_row<VEC>(a.xin, xrow(gr + 1), cw, g.W, xS);
-        if (PHASE) load_reflect_row<VEC>(a.phase, prow(gr + 1), cw, g.W, pS);
+      if (M::NEED_LAP) load_enforced_row<VEC>(a.xin, xrow(gr + 1), cw, g.W, xS);
+      // Phase field: the term is identically 0 wherever phi is locally constant (most of the
+      // domain: phi == 1 away from the holes), so phi is only fetched for the 32-column blocks
+      // that fib_set_phase flagged; there it is read on demand (no marching window).
+      float pN[VEC], pS[VEC], pC[VEC + 2];
+      bool ph = false;
+      if (PHASE && M::NEED_LAP) {
+        ph = a.pmask[(gr - g.row0) * a.pmask_pitch + (c >> 5)] != 0;
+        if (ph) {
+          VecIO<VEC>::ld(a.phase + (prow(gr - 1) + c), pN);
+          VecIO<VEC>::ld(a.phase + (prow(gr + 1) + c), pS);
+          load_reflect_row<VEC>(a.phase, prow(gr), cw, g.W, pC);
+        }
       }
       // raw centre values: differ from the enforced ones only on the global border ring
       float xraw[VEC];
@@ -96,9 +101,9 @@ step_kernel(const Geom g, const StepArgs<M> a) {
         if (M::NEED_LAP) {
           lap = lap9(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], xN[l], xS[l], xN[l + 2], xS[l + 2],
                      xC[l + 1]);
-          if (PHASE)
-            lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l + 1],
-                                            pS[l + 1], pC[l], pC[l + 2], pC[l + 1]));
+          if (PHASE && ph)
+            lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l], pS[l],
+                                            pC[l], pC[l + 2], pC[l + 1]));
         }
         float sl[M::NS > 0 ? M::NS : 1];
 #pragma unroll
@@ -115,10 +120,6 @@ step_kernel(const Geom g, const StepArgs<M> a) {
       if (M::NEED_LAP) {
 #pragma unroll
         for (int j = 0; j < VEC + 2; ++j) { xN[j] = xC[j]; xC[j] = xS[j]; }
-        if (PHASE) {
-#pragma unroll
-          for (int j = 0; j < VEC + 2; ++j) { pN[j] = pC[j]; pC[j] = pS[j]; }
-        }
       } else if (i + 1 < R && gr + 1 < gend) {
         load_enforced_row<VEC>(a.xin, xrow(gr + 1), cw, g.W, xC);
       }

@@ -75,7 +75,7 @@ __device__ __forceinline__ float phase_term(float xN, float xS, float xW, float 
                                             float pS, float pW, float pE, float pC) {
   float a = __fmul_rn(__fsub_rn(xS, xN), __fsub_rn(pS, pN));
   float b = __fmul_rn(__fsub_rn(xE, xW), __fsub_rn(pE, pW));
-  return __fdiv_rn(__fadd_rn(a, b), __fmul_rn(4.0f, pC));
+  return m_div(__fadd_rn(a, b), __fmul_rn(4.0f, pC));   // 2-ulp SFU division (IEEE with FIB_ACCURATE_MATH)
 }
 
 }  // namespace fib
