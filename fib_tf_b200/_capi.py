@@ -70,6 +70,8 @@ _SIGNATURES = {
     'fib_stimulate': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
     'fib_probe': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _FP]),
     'fib_weighted_sum': (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    'fib_set_weights': (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),
+    'fib_masked_sum': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'fib_sync': (C.c_int, [_P]),
     'fib_timer_start': (C.c_int, [_P]),
     'fib_timer_stop': (C.c_int, [_P]),
@@ -236,6 +238,15 @@ class Context:
     def weighted_sum(self, var):
         a, b = C.c_double(), C.c_double()
         check(lib().fib_weighted_sum(self._h, self.var(var), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_weights(self, slot, rows, first_row=0):
+        a, p = _f32c(rows)
+        check(lib().fib_set_weights(self._h, slot, p, int(first_row), a.shape[0]))
+
+    def masked_sum(self, var, slot):
+        a, b = C.c_double(), C.c_double()
+        check(lib().fib_masked_sum(self._h, self.var(var), slot, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def sync(self):

@@ -122,6 +122,7 @@ struct fib_ctx {
   uint64_t launches = 0;
   std::vector<GraphKey> graphs;
   double* red = nullptr;              // 2 doubles for reductions
+  float* weights[4] = {nullptr, nullptr, nullptr, nullptr};   // user masks, halo layout like phase
   // NCCL
   void* comm = nullptr;
   int nranks = 1, rank = 0;
@@ -324,6 +325,7 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->lut);
   cudaFree(c->lut_t);
   cudaFree(c->red);
+  for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
   cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev_stop);
   cudaEventDestroy(c->ev_bnd);
@@ -848,13 +850,18 @@ extern "C" int fib_probe(fib_ctx* c, int var, int row, int col, float* out) {
   return 0;
 }
 
+static int reduce_weighted(fib_ctx* c, int var, const float* w, double* sum_wx, double* sum_w);
 extern "C" int fib_weighted_sum(fib_ctx* c, int var, double* sum_wx, double* sum_w) {
   if (!c || !sum_wx || !sum_w) return fail(FIB_E_ARG, "NULL argument");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
+  return reduce_weighted(c, var, c->phase, sum_wx, sum_w);
+}
+
+static int reduce_weighted(fib_ctx* c, int var, const float* w, double* sum_wx, double* sum_w) {
   CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
   const float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
-  wsum_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(base, c->phase, c->g, var == 0 ? 1 : 0, c->red);
+  wsum_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(base, w, c->g, var == 0 ? 1 : 0, c->red);
   CU(cudaGetLastError());
   c->launches++;
   double h[2];
@@ -863,6 +870,31 @@ extern "C" int fib_weighted_sum(fib_ctx* c, int var, double* sum_wx, double* sum
   *sum_wx = h[0];
   *sum_w = h[1];
   return 0;
+}
+
+extern "C" int fib_set_weights(fib_ctx* c, int slot, const float* rows_host, int first_row, int nrows) {
+  if (!c || !rows_host) return fail(FIB_E_ARG, "ctx/rows is NULL");
+  if (slot < 0 || slot >= 4) return fail(FIB_E_ARG, "weight slot %d out of range 0..3", slot);
+  if (first_row > c->g.row0 || first_row + nrows < c->g.row0 + c->g.rows)
+    return fail(FIB_E_ARG, "weight rows [%d,%d) do not cover this shard", first_row, first_row + nrows);
+  DevGuard dg(c->cfg.device);
+  if (!c->weights[slot]) {
+    CU(cudaMalloc(&c->weights[slot], c->halo_floats() * sizeof(float)));
+    CU(cudaMemsetAsync(c->weights[slot], 0, c->halo_floats() * sizeof(float), c->stream));
+  }
+  CU(cudaMemcpy2DAsync(c->weights[slot] + c->g.pitch, c->g.pitch * sizeof(float),
+                       rows_host + (size_t)(c->g.row0 - first_row) * c->g.W, c->g.W * sizeof(float),
+                       c->g.W * sizeof(float), c->g.rows, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_masked_sum(fib_ctx* c, int var, int slot, double* sum_wx, double* sum_w) {
+  if (!c || !sum_wx || !sum_w) return fail(FIB_E_ARG, "NULL argument");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (slot < 0 || slot >= 4 || !c->weights[slot]) return fail(FIB_E_STATE, "weight slot %d is empty", slot);
+  DevGuard dg(c->cfg.device);
+  return reduce_weighted(c, var, c->weights[slot], sum_wx, sum_w);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -311,6 +311,31 @@ class IonicModel:
         return self
 
     # ---- extras ---------------------------------------------------------------------------------
+    def add_probe_mask(self, mask):
+        """Registers an [H, W] weight plane on the device (at most 4) and returns its slot; use
+        with masked_image_mean().  Backs the pseudo-electrograms of the reference's egm.py."""
+        if not self.defined:
+            raise AssertionError('add_probe_mask should be called after calling define')
+        slot = len(self.__dict__.setdefault('_mask_slots', []))
+        m = np.asarray(mask, dtype=np.float32)
+        self._ctx.set_weights(slot, m[self._row0:self._row0 + self._rows], self._row0)
+        self._mask_slots.append(slot)
+        return slot
+
+    def masked_image_mean(self, slot):
+        """np.mean(self.image() * mask) (egm.py:44-47) without moving the frame to the host:
+        one weighted reduction on the device (summed over ranks when sharded)."""
+        swx, sw = self._ctx.masked_sum(self._pot_name, slot)
+        if self._nranks > 1:
+            import torch.distributed as dist
+            parts = [None] * self._nranks
+            dist.all_gather_object(parts, (swx, sw))
+            swx, sw = sum(p[0] for p in parts), sum(p[1] for p in parts)
+        # image = (V - min_v) / (max_v - min_v) for BR / Courtemanche, V itself for 4v
+        if self.MODEL_ID != _capi.FENTON4V:
+            swx = (swx - self.min_v * sw) / (self.max_v - self.min_v)
+        return swx / (self.height * self.width)
+
     def sync(self):
         self._ctx.sync()
 

@@ -151,6 +151,11 @@ int fib_probe(fib_ctx *ctx, int var, int row, int col, float *out);
 /* weighted mean of a plane over this shard: sum(w*x), sum(w) (w = phase field, or 1 if none):
  * backs np.average(x, weights=phase) in court_ultra.py:466-480.  Synchronous. */
 int fib_weighted_sum(fib_ctx *ctx, int var, double *sum_wx, double *sum_w);
+/* user weight planes (pseudo-electrogram masks, egm.py:5-12,44-47: np.mean(image * mask)):
+ * fib_set_weights uploads global rows [first_row, first_row+nrows) of an [H][W] mask into `slot`
+ * (0..3; must cover this shard); fib_masked_sum returns sum(mask*x) and sum(mask) over the shard. */
+int fib_set_weights(fib_ctx *ctx, int slot, const float *rows_host, int first_row, int nrows);
+int fib_masked_sum(fib_ctx *ctx, int var, int slot, double *sum_wx, double *sum_w);
 
 /* ---- sync / timing / accounting ------------------------------------------------------------ */
 int fib_sync(fib_ctx *ctx);

@@ -316,3 +316,37 @@ def test_lut_path_against_the_compiled_reference_header(cuda):
     for k, name in enumerate(names):
         e = onp.rel_err(got[:, :, k], want[:, :, k], onp.var_floor('court_ultra', name))
         assert e <= 1e-3, (name, e)
+
+
+def test_run_generator_observers_and_masked_means(cuda):
+    """The drop-in driver loop: run() yields, fire_op between iterations, the headless cycle-length
+    probe, keep_state, a Screen stand-in, and the on-device pseudo-EGM reduction against NumPy."""
+    from fib_tf_b200.br import BeelerReuter
+    from fib_tf_b200.egm import create_mask
+    from fib_tf_b200.screen import Screen
+    cfg = {'width': 64, 'height': 64, 'dt': 0.1, 'dt_per_plot': 5, 'diff': 0.809, 'duration': 30,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': True}
+    m = BeelerReuter(cfg)
+    m.add_hole_to_phase_field(50, 50, 7)
+    m.define()
+    m.add_pace_op('s2', 'top', 10.0)
+    slot = m.add_probe_mask(create_mask(m, 24, 30, 6))
+    seen, spikes = [], []
+    m.cl_observer = lambda i, cl: spikes.append((i, cl))
+    im = Screen(m.height, m.width, 'test')
+    for i in m.run(im, block=False):
+        seen.append(i)
+        if i == 3:
+            m.fire_op('s2')
+    assert seen == list(range(m.samples)) and m.samples == 60
+    assert im.frames_shown == 60 and im.last.shape == (64, 64)
+    assert len(spikes) == 1 and 30 < spikes[0][0] < 60      # the S1 wave reaches [20, W//2] at ~24 ms
+    img = m.image()
+    want = float(np.mean(img * create_mask(m, 24, 30, 6)))
+    got = m.masked_image_mean(slot)
+    assert abs(got - want) <= 1e-5 * abs(want) + 1e-9
+    # phase-weighted mean (court_ultra.py:466-480)
+    swx, sw = m._ctx.weighted_sum('M')
+    mm = m._State['M'].eval()
+    assert abs(swx / sw - np.average(mm, weights=m.phase)) <= 1e-5
+    m.close()

@@ -102,3 +102,15 @@ def test_chebyshev_table_equals_oracle_and_reference_coefficients():
 def test_graph_builder_helpers_are_explicitly_out_of_scope():
     with pytest.raises(NotImplementedError):
         Fenton4v(CFG).laplace(None)
+
+
+def test_headless_screen_keeps_the_reference_protocol(tmp_path):
+    from fib_tf_b200.screen import Screen
+    im = Screen(4, 6, 'x', keep_every=2)
+    for k in range(3):
+        assert im.imshow(np.full([4, 6], 0.25 * k, np.float32))
+    assert im.frames_shown == 3 and len(im.frames) == 2 and im.peek() and im.wait() is None
+    with pytest.raises(ValueError):
+        im.imshow(np.zeros([3, 3]))
+    saved = im.save(str(tmp_path / 'frame.npy'))
+    assert np.array_equal(np.load(saved), im.last)
