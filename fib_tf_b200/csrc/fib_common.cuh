@@ -19,14 +19,27 @@ struct Geom {
   int pitch;        // floats per row
 };
 
+// FIB_NC_LOADS=1 reads the planes through the non-coherent path (ld.global.nc).  In-place planes are
+// read exactly once, by the thread that later overwrites the same address, and L1 is invalidated at
+// every launch boundary, so no stale line can ever be observed; what it buys is freedom for the
+// scheduler to hoist the next row's loads above the current row's stores (memory-level parallelism).
+#ifndef FIB_NC_LOADS
+#define FIB_NC_LOADS 1
+#endif
+#if FIB_NC_LOADS
+#define FIB_LD(p) __ldg(p)
+#else
+#define FIB_LD(p) (*(p))
+#endif
+
 template <int VEC> struct VecIO;
 template <> struct VecIO<1> {
-  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = *p; }
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = FIB_LD(p); }
   static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
 };
 template <> struct VecIO<2> {
   static __device__ __forceinline__ void ld(const float* p, float* v) {
-    float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    float2 t = FIB_LD(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
   }
   static __device__ __forceinline__ void st(float* p, const float* v) {
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
@@ -34,7 +47,7 @@ template <> struct VecIO<2> {
 };
 template <> struct VecIO<4> {
   static __device__ __forceinline__ void ld(const float* p, float* v) {
-    float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    float4 t = FIB_LD(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ void st(float* p, const float* v) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -149,16 +149,23 @@ inline cudaError_t launch_step_p(const Geom& g, const StepArgs<M>& a, cudaStream
   if (force == 4 && M::MAX_R >= 4) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
   if (force == 2 && M::MAX_R >= 2) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);
   if (force == 1) return launch_step_r<M, VEC, 1, BY, PHASE>(g, a, st);
-  if (M::MAX_R >= 8 && blocks(8) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 8 ? 8 : 1), BY, PHASE>(g, a, st);
-  if (M::MAX_R >= 4 && blocks(4) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
-  if (M::MAX_R >= 2 && blocks(2) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);
+  if (M::MAX_R >= 8 && M::AUTO_R >= 8 && blocks(8) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 8 ? 8 : 1), BY, PHASE>(g, a, st);
+  if (M::MAX_R >= 4 && M::AUTO_R >= 4 && blocks(4) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 4 ? 4 : 1), BY, PHASE>(g, a, st);
+  if (M::MAX_R >= 2 && M::AUTO_R >= 2 && blocks(2) >= want) return launch_step_r<M, VEC, (M::MAX_R >= 2 ? 2 : 1), BY, PHASE>(g, a, st);
   return launch_step_r<M, VEC, 1, BY, PHASE>(g, a, st);
 }
 
 template <class M>
 inline cudaError_t launch_step(const Geom& g, const StepArgs<M>& a, cudaStream_t st, int sms) {
   if (a.nrows <= 0) return cudaSuccess;
-  if (a.phase && M::NEED_LAP) return launch_step_p<M, M::VEC, M::BY, true>(g, a, st, sms);
+  const bool ph = a.phase && M::NEED_LAP;
+  // Small grids (<= 2^20 cells, e.g. the reference's 512^2 configs) cannot fill 148 SMs with the
+  // wide flavour: fall back to one cell per thread there (twice the CTAs, no tail wave).
+  if (M::VEC > 1 && M::VEC_SMALL != M::VEC && (long)a.nrows * g.W <= (1L << 20)) {
+    if (ph) return launch_step_p<M, M::VEC_SMALL, M::BY, true>(g, a, st, sms);
+    return launch_step_p<M, M::VEC_SMALL, M::BY, false>(g, a, st, sms);
+  }
+  if (ph) return launch_step_p<M, M::VEC, M::BY, true>(g, a, st, sms);
   return launch_step_p<M, M::VEC, M::BY, false>(g, a, st, sms);
 }
 

@@ -37,11 +37,11 @@ __device__ __forceinline__ void load_enforced_row(const float* __restrict__ x, i
   if (cw.interior_x) {
     const float* p = x + (row + cw.c);
     VecIO<VEC>::ld(p, &e[1]);
-    e[0] = p[-1];
-    e[VEC + 1] = p[VEC];
+    e[0] = FIB_LD(p - 1);
+    e[VEC + 1] = FIB_LD(p + VEC);
   } else {
 #pragma unroll
-    for (int j = 0; j < VEC + 2; ++j) e[j] = x[row + clampi(cw.c - 1 + j, 1, W - 2)];
+    for (int j = 0; j < VEC + 2; ++j) e[j] = FIB_LD(x + (row + clampi(cw.c - 1 + j, 1, W - 2)));
   }
 }
 

@@ -17,16 +17,16 @@
 // kernels are issue/latency bound, so occupancy beats per-thread vector width.  The step that also
 // advances the four slow gates holds more live values than the fast-only step of the skip schedule.
 #ifndef FIB_BR_VEC_SLOW
-#define FIB_BR_VEC_SLOW 1
+#define FIB_BR_VEC_SLOW 2
 #endif
 #ifndef FIB_BR_MINB_SLOW
-#define FIB_BR_MINB_SLOW 8
+#define FIB_BR_MINB_SLOW 6
 #endif
 #ifndef FIB_BR_VEC_FAST
 #define FIB_BR_VEC_FAST 2
 #endif
 #ifndef FIB_BR_MINB_FAST
-#define FIB_BR_MINB_FAST 6
+#define FIB_BR_MINB_FAST 8
 #endif
 
 namespace fib {
@@ -84,8 +84,10 @@ template <bool CHEBY, bool SLOW>
 struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
   static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
+  static constexpr int VEC_SMALL = 1;   // cells per thread on grids <= 2^20 cells
   static constexpr int BY = 4;
-  static constexpr int MAX_R = 2;
+  static constexpr int MAX_R = 4;
+  static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS = SLOW ? FIB_BR_MINB_SLOW : FIB_BR_MINB_FAST;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
   static constexpr bool NEED_LAP = true;

@@ -186,8 +186,10 @@ template <int MODE, bool LUT, bool US>
 struct Courtemanche {
   static constexpr int NS = S_COUNT;      // 21 slots; S_us only used when US
   static constexpr int VEC = 1;
+  static constexpr int VEC_SMALL = 1;   // cells per thread on grids <= 2^20 cells
   static constexpr int BY = 4;
   static constexpr int MAX_R = LUT ? 2 : 1;
+  static constexpr int AUTO_R = LUT ? 2 : 1;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
       MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
   static constexpr bool NEED_RAW = false; // V = enforce_boundary(V0) everywhere (court.py:126-127)

@@ -4,7 +4,7 @@
 #include "fib_kernels.cuh"
 
 #ifndef FIB_4V_MINB
-#define FIB_4V_MINB 7
+#define FIB_4V_MINB 8
 #endif
 
 namespace fib {
@@ -12,8 +12,10 @@ namespace fib {
 struct Fenton4v {
   static constexpr int NS = 3;            // V, W, S  (U is the diffusing variable)
   static constexpr int VEC = 4;
+  static constexpr int VEC_SMALL = 4;   // cells per thread on grids <= 2^20 cells
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
+  static constexpr int AUTO_R = 4;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS = FIB_4V_MINB;
   static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
   static constexpr bool NEED_LAP = true;
