@@ -350,3 +350,43 @@ def test_run_generator_observers_and_masked_means(cuda):
     mm = m._State['M'].eval()
     assert abs(swx / sw - np.average(mm, weights=m.phase)) <= 1e-5
     m.close()
+
+
+def test_checkpoint_restart_and_timeline(cuda, tmp_path):
+    """run(keep_state=True) -> model.state dict -> np.save / np.load -> define(state=...)
+    (ionic.py:226-229, court.py:49-56, court_ultra.py:511,518): the restarted run must continue
+    bit-identically; config['timeline'] writes a chrome trace and advances the state once more
+    (ionic.py:231-241)."""
+    import json as _json
+    from fib_tf_b200.court import Courtemanche
+    cfg = {'width': 40, 'height': 24, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.809, 'duration': 2,
+           'timeline': False, 'timeline_name': str(tmp_path / 'trace.json'), 'save_graph': False}
+
+    def drive(m, **kw):
+        for i in m.run(None, block=False, **kw):
+            if i % 10 == 0:
+                m.fire_op('slow')
+
+    whole = Courtemanche(dict(cfg, duration=4))
+    whole.add_hole_to_phase_field(20, 12, 4)
+    whole.define()
+    drive(whole)
+    a = Courtemanche(cfg)
+    a.add_hole_to_phase_field(20, 12, 4)
+    a.define()
+    drive(a, keep_state=True)
+    np.save(str(tmp_path / 'state_small'), a.state)
+    state = np.load(str(tmp_path / 'state_small.npy'), allow_pickle=True).item(0)
+    assert sorted(state) == sorted(a._ctx.var_names)
+    b = Courtemanche(dict(cfg, timeline=True))
+    b.add_hole_to_phase_field(20, 12, 4)
+    b.define(s1=False, state=state)
+    drive(b)
+    trace = _json.load(open(cfg['timeline_name']))
+    assert trace['traceEvents'][0]['dur'] > 0
+    # b ran 20 + 1 traced iterations after the restart: advance `whole` by the same extra step
+    whole._ctx.step(0, 1)
+    for v in whole._ctx.var_names:
+        assert np.array_equal(whole._State[v].eval(), b._State[v].eval()), v
+    for m in (whole, a, b):
+        m.close()
