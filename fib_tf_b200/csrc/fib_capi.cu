@@ -142,7 +142,7 @@ struct DevGuard {
 // small kernels
 // ------------------------------------------------------------------------------------------
 // ionic.py:144-163: X := max(X, s) with s = value inside the rectangle and floor_v elsewhere.
-// (m > x ? m : x) keeps a NaN in x, like tf.maximum.
+// fmaxf: tf.maximum on the reference's GPU target returns the non-NaN operand (see clip_tf).
 __global__ void stim_kernel(float* __restrict__ x, Geom g, int halo, int r0, int r1, int c0, int c1,
                             float value, float floor_v) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +152,7 @@ __global__ void stim_kernel(float* __restrict__ x, Geom g, int halo, int r0, int
     const float m = (gr >= r0 && gr < r1 && c >= c0 && c < c1) ? value : floor_v;
     float* p = x + (size_t)(lr + halo) * g.pitch + c;
     const float v = *p;
-    *p = m > v ? m : v;
+    *p = fmaxf(v, m);
   }
 }
 

@@ -2,6 +2,7 @@
 // sm_100a only.  No CPU fallback exists anywhere in this library.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "fib_math.cuh"
@@ -54,31 +55,38 @@ template <> struct VecIO<4> {
   }
 };
 
-// tf.clip_by_value(x, lo, hi) == min(max(x, lo), hi) with NaN propagating (ionic.py:122-123,
-// br.py:167-168).  fminf/fmaxf would swallow a NaN; the reference does not.
-__device__ __forceinline__ float clip_nan(float x, float lo, float hi) {
-  return min_nan(max_nan(x, lo), hi);
+// tf.clip_by_value(x, lo, hi) = maximum(minimum(x, hi), lo) (ionic.py:122-123, br.py:167-168) with the
+// NaN behaviour of the reference's TARGET, TensorFlow on the GPU: Eigen's CUDA mini/maxi are
+// fminf/fmaxf (and XLA:GPU lowered min/max to minnum/maxnum), which return the non-NaN operand.
+// This matters: the BR currents are 0/0 when V hits -23.0f (or -47.0f) exactly (br.py:150-151,
+// 52), which happens to a few cells of a 512^2 grid in every repolarisation wave; on the GPU the
+// clip turns that NaN into the upper bound for one step and the run goes on (docs/br.png), whereas
+// NaN-propagating min/max (NumPy, TF on the CPU) would poison the whole grid within 50 ms.
+__device__ __forceinline__ float clip_tf(float x, float lo, float hi) {
+  return fmaxf(fminf(x, hi), lo);
 }
 
 // IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).
 // neg_dt = fp32(-dt) (or fp32(-(dt*n)) folded in double on the host, br.py:197-200).
 __device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, float neg_dt) {
   float e = m_expm1(m_div(neg_dt, tau));
-  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 // Rush-Larsen with caller-supplied clip bounds: (1e-5, 0.99999) for the Python models, (-inf, +inf)
 // for the native courtemanche.h rule, which does not clip (courtemanche.h:287-292)
 __device__ __forceinline__ float rush_larsen_b(float g, float g_inf, float tau, float neg_dt, float lo,
                                                float hi) {
-  float e = m_expm1(m_div(neg_dt, tau));
-  return clip_nan(fmaf(g - g_inf, e, g), lo, hi);
+  const float e = m_expm1(m_div(neg_dt, tau));
+  const float r = fmaf(g - g_inf, e, g);
+  return lo == -INFINITY ? r : clip_tf(r, lo, hi);      // uniform select; no clip in native mode
 }
 __device__ __forceinline__ float rush_larsen_eb(float g, float g_inf, float e, float lo, float hi) {
-  return clip_nan(fmaf(g - g_inf, e, g), lo, hi);
+  const float r = fmaf(g - g_inf, e, g);
+  return lo == -INFINITY ? r : clip_tf(r, lo, hi);
 }
 // same with e = expm1(-dt/tau) precomputed (Python-scalar tau: court.py:189,243)
 __device__ __forceinline__ float rush_larsen_e(float g, float g_inf, float e) {
-  return clip_nan(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 
 }  // namespace fib

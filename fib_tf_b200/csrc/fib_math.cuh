@@ -83,17 +83,4 @@ __device__ __forceinline__ float m_half_1p_tanh(float z) {
 }
 #endif
 
-// NaN-propagating min / max (PTX min.NaN / max.NaN, one FMNMX each): tf.clip_by_value and
-// tf.maximum return NaN when the data operand is NaN, fminf / fmaxf would swallow it.
-__device__ __forceinline__ float max_nan(float a, float b) {
-  float r;
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ float min_nan(float a, float b) {
-  float r;
-  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
-
 }  // namespace fib

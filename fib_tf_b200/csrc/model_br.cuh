@@ -167,7 +167,7 @@ struct BeelerReuter {
     const float I_sum = iK1 + ix1 + iNa + iCa;
     // (V0 + ddt*lap) - dt*I_sum/C_m with the reference's rounding sequence (br.py:167-168): the
     // result crosses 0 mV while the operands are ~80 mV, so no FMA contraction here
-    Vnew = clip_nan(__fsub_rn(__fadd_rn(V0, __fmul_rn(p.ddt, lap)), __fmul_rn(p.dt, I_sum)), -85.0f,
+    Vnew = clip_tf(__fsub_rn(__fadd_rn(V0, __fmul_rn(p.ddt, lap)), __fmul_rn(p.dt, I_sum)), -85.0f,
                     25.0f);
     const float dC = -1.0e-7f * iCa + 0.07f * (1.0e-7f - C);
     s[0] = fmaf(p.dt, dC, C);

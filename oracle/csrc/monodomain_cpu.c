@@ -51,7 +51,8 @@ static inline float x0_at(const float* X, int H, int W, int r, int c) {
   return X[(size_t)clampi(r, 1, H - 2) * W + clampi(c, 1, W - 2)];
 }
 
-static inline float clipf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* tf.clip_by_value on the reference's GPU target: fmax(fmin(x, hi), lo), the non-NaN operand wins */
+static inline float clipf(float x, float lo, float hi) { return fmaxf(fminf(x, hi), lo); }
 
 /* ionic.py:115-123 */
 static inline float rush_larsen(float g, float g_inf, float tau, float neg_dt) {

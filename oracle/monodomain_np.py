@@ -47,13 +47,20 @@ def laplace(X0, phase=None):
     return lap
 
 
+def clip_by_value(x, lo, hi):
+    """tf.clip_by_value = maximum(minimum(x, hi), lo) with the NaN behaviour of the reference's GPU
+    target (Eigen's CUDA mini/maxi = fminf/fmaxf: the non-NaN operand wins), see
+    fib_tf_b200/csrc/fib_common.cuh.  np.fmin/np.fmax have exactly those semantics."""
+    return np.fmax(np.fmin(x, F32(hi)), F32(lo))
+
+
 def rush_larsen(g, g_inf, tau, dt):
     """ionic.py:115-123 -- clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999)."""
     if isinstance(tau, np.ndarray):
         e = np.expm1(F32(-dt) / tau)
     else:                                   # Python-scalar tau: folded in Python, then fp32
         e = np.expm1(F32(-dt / tau))
-    return np.minimum(np.maximum(g + (g - g_inf) * e, F32(0.00001)), F32(0.99999))
+    return clip_by_value(g + (g - g_inf) * e, 0.00001, 0.99999)
 
 
 def hole_phase(phase, height, width, x, y, radius, neg=False):
@@ -89,7 +96,7 @@ def apply_pace(X, loc, v, min_v):
     if reg is not None:
         r0, r1, c0, c1 = reg
         s[max(r0, 0):r1, max(c0, 0):c1] = v
-    return np.maximum(X, s)
+    return np.fmax(X, s)       # tf.maximum on the GPU target: the non-NaN operand wins
 
 
 # --------------------------------------------------------------------------
@@ -258,7 +265,7 @@ def br_step(st, dt, diff, n=1, cheby=False, coeffs=None, phase=None):
     iCa = C_s * g_s * D * Fg * (V0 - ECa)
     I_sum = iK1 + ix1 + iNa + iCa
     V1 = V0 + diff * dt * laplace(V0, phase) - dt * I_sum / C_m
-    new['V'] = np.minimum(np.maximum(V1, F32(-85.0)), F32(25.0))
+    new['V'] = clip_by_value(V1, -85.0, 25.0)
     dC = -1.0e-7 * iCa + 0.07 * (1.0e-7 - C)
     new['C'] = C + dt * dC
     return new

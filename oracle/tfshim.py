@@ -238,12 +238,14 @@ def pow(x, y, name=None):       # noqa: A001
     return Node(_pow, [x, y])
 
 
+# min / max follow the reference's GPU target (Eigen's CUDA mini/maxi are fminf/fmaxf; XLA:GPU used
+# minnum/maxnum): the non-NaN operand wins.  np.fmin / np.fmax have exactly those semantics.
 def maximum(x, y, name=None):
-    return Node(lambda a, b: np.maximum(_coerce(a), _coerce(b)), [x, y])
+    return Node(lambda a, b: np.fmax(_coerce(a), _coerce(b)), [x, y])
 
 
 def minimum(x, y, name=None):
-    return Node(lambda a, b: np.minimum(_coerce(a), _coerce(b)), [x, y])
+    return Node(lambda a, b: np.fmin(_coerce(a), _coerce(b)), [x, y])
 
 
 def where(cond, x, y, name=None):
@@ -251,7 +253,8 @@ def where(cond, x, y, name=None):
 
 
 def clip_by_value(x, lo, hi, name=None):
-    return Node(lambda a: np.minimum(np.maximum(_coerce(a), _coerce(lo)), _coerce(hi)), [x])
+    # TF 1.x: maximum(minimum(t, clip_value_max), clip_value_min)
+    return Node(lambda a: np.fmax(np.fmin(_coerce(a), _coerce(hi)), _coerce(lo)), [x])
 
 
 def pad(x, paddings, mode='CONSTANT', name=None):

@@ -390,3 +390,20 @@ def test_checkpoint_restart_and_timeline(cuda, tmp_path):
         assert np.array_equal(whole._State[v].eval(), b._State[v].eval()), v
     for m in (whole, a, b):
         m.close()
+
+
+@pytest.mark.parametrize('module,frames', [('fib_tf_b200.fenton', 100), ('fib_tf_b200.br', 100)])
+def test_reference_driver_blocks_run_unchanged(cuda, module, frames, tmp_path, monkeypatch):
+    """The `__main__` blocks of the drop-in modules are the reference's own driver loops
+    (fenton.py:155-187, br.py:347-382: 512^2, 1000 ms, hole, S2 at 210/300 ms, a frame into
+    cube.npy every 10 ms).  They must run headless and leave a re-entrant wave behind."""
+    import runpy
+    monkeypatch.chdir(tmp_path)
+    runpy.run_module(module, run_name='__main__')
+    cube = np.load(str(tmp_path / 'cube.npy'), mmap_mode='r')
+    assert cube.shape == (frames, 512, 512)
+    last = np.asarray(cube[-1])
+    assert np.isfinite(last).all() and 0.0 <= last.min() and last.max() <= 1.0 + 1e-6
+    # activity persists long after S1 (10 ms) and S2 died out only if the S1-S2 protocol produced a
+    # spiral: an excited region (image > 0.5) is still present in the last frames
+    assert (np.asarray(cube[-10:]) > 0.5).mean() > 0.01
