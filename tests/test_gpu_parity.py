@@ -407,3 +407,43 @@ def test_reference_driver_blocks_run_unchanged(cuda, module, frames, tmp_path, m
     # activity persists long after S1 (10 ms) and S2 died out only if the S1-S2 protocol produced a
     # spiral: an excited region (image > 0.5) is still present in the last frames
     assert (np.asarray(cube[-10:]) > 0.5).mean() > 0.01
+
+
+@pytest.mark.parametrize('ultra', [False, True])
+def test_courtemanche_driver_loops_stay_finite(cuda, ultra):
+    """The driver loops of court.py:582-636 / court_ultra.py:489-512 (holes incl. neg=True, S2,
+    'slow' every 10th iteration, 'trend', cl_observer, keep_state) for 600 ms at 256^2: finite
+    state, a propagated S1 wave, gates inside their clip range."""
+    from functools import partial
+    from fib_tf_b200 import court, court_ultra
+    cfg = {'width': 256, 'height': 256, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5 if ultra else 0.809,
+           'duration': 600, 'skip': False, 'cheby': True, 'timeline': False,
+           'timeline_name': 'unused.json', 'save_graph': False, 'ultra_slow': ultra}
+    mod = court_ultra if ultra else court
+    m = mod.Courtemanche(cfg)
+    m.add_hole_to_phase_field(128, 128, 15)
+    m.add_hole_to_phase_field(128, 128, 122, neg=True)
+    m.define()
+    m.add_pace_op('s2', 'luq', 10.0)
+    log = []
+    m.cl_observer = partial(court_ultra.cl_observer, m, log, 0) if ultra else \
+        (lambda i, cl: log.append((i, cl)))
+    s2 = m.millisecond_to_step(300)
+    trend = []
+    for i in m.run(None, keep_state=True, block=False):
+        if i % 10 == 0:
+            m.fire_op('slow')
+            m.fire_op('trend')
+            trend.append(m._Trend.eval())
+        if i == s2:
+            m.fire_op('s2')
+    trend = np.asarray(trend)
+    assert np.isfinite(trend).all() and trend[:, 0].max() > -20.0        # the wave passed the probe
+    assert sorted(m.state) == sorted(m._ctx.var_names)
+    for name, a in m.state.items():
+        assert np.isfinite(a).all(), name
+    for g in ('_m_', '_h_', '_j_', '_d_', '_f_', '_u_', '_v_', '_w_'):
+        assert 1e-5 <= m.state[g].min() and m.state[g].max() <= 0.99999 + 1e-7, g
+    q = m.calc_inter(-50.0)
+    assert abs(q['m_inf'] - 0.268253) < 1e-5 and abs(q['i_NaCab'] - 102066.71) < 1.0   # SURVEY B.4
+    m.close()
