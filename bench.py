@@ -14,7 +14,7 @@ owns 32768/N rows.  Rank 0 prints exactly ONE JSON line on stdout.
             HBM; the state (16 GiB) is >> the 126 MB L2, so no flush is needed between steps.
   e2e       the same K iterations through the public drop-in API (Fenton4v.run() generator) with
             HOST buffers inside the timed region: strip-wise upload of the full initial state
-            from pinned memory (H2D), the headless cycle-length probe every iteration (D2H) and a
+            (16 GiB at 32768^2) from pinned memory (H2D), the headless cycle-length probe every iteration (D2H) and a
             full-frame grab into pinned memory every 10th iteration (the cadence of fenton.py:184).
   roofline  HBM-bound: 32 B per cell-step (4 fp32 planes read + written once) x cells per launch
             / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
@@ -82,13 +82,25 @@ def strips_of(tile_plane, width):
     return even, even[::-1]
 
 
-def upload_tiled(ctx, tile, row0, rows, width, pinned):
-    """Strip-wise H2D upload of the mirror-tiled state for global rows [row0, row0+rows)."""
-    nbytes = 0
+def pinned_strips(tile, width):
+    """The synthetic input as it sits in page-locked host memory: per state variable the two
+    [512, width] strips (even / odd tile rows) of the mirror-tiled field."""
+    from fib_tf_b200 import _capi
+    out = {}
     for name, plane in tile.items():
         even, odd = strips_of(plane, width)
-        pinned[0][:] = even
-        pinned[1][:] = odd
+        bufs = [_capi.pinned_empty((TILE, width)), _capi.pinned_empty((TILE, width))]
+        bufs[0][:] = even
+        bufs[1][:] = odd
+        out[name] = bufs
+    return out
+
+
+def upload_tiled(ctx, strips, row0, rows, width):
+    """Strip-wise H2D upload (from pinned memory) of the mirror-tiled state for global rows
+    [row0, row0+rows): every 512-row block of every plane is one fib_set_rect."""
+    nbytes = 0
+    for name, pinned in strips.items():
         g = row0
         while g < row0 + rows:
             t, r = divmod(g, TILE)
@@ -286,8 +298,8 @@ def main():
     model.define(s1=False)
     ctx = model._ctx
     row0, rows = model._row0, model._rows
-    pinned = [_capi.pinned_empty((TILE, size)), _capi.pinned_empty((TILE, size))]
-    upload_tiled(ctx, tile, row0, rows, size, pinned)
+    strips = pinned_strips(tile, size)
+    upload_tiled(ctx, strips, row0, rows, size)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -312,12 +324,15 @@ def main():
     d2h = 0
     barrier()
     t0 = time.perf_counter()
-    h2d = upload_tiled(ctx, tile, row0, rows, size, pinned)
+    h2d = upload_tiled(ctx, strips, row0, rows, size)
     with contextlib.redirect_stdout(sys.stderr):
         for i in model.run(None):
             if i % 10 == 0:                               # frame grab cadence of fenton.py:184
-                ctx.get_state('U', out=frame)
+                if i:
+                    model.image_wait()
+                model.image_async(frame)                  # pinned target, overlaps the next steps
                 d2h += frame.nbytes
+        model.image_wait()
     d2h += 4 * K                                          # the per-iteration probe read
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -358,7 +373,7 @@ def main():
         line['cpu_baseline'] = info
     if rank == 0:
         print(json.dumps(line), flush=True)
-    for p in pinned + [frame]:
+    for p in [b for bufs in strips.values() for b in bufs] + [frame]:
         _capi.pinned_free(p)
     model.close()
     if world > 1:

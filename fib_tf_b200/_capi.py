@@ -59,6 +59,8 @@ _SIGNATURES = {
     'fib_set_state': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_state': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_rect': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'fib_snapshot_begin': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    'fib_snapshot_wait': (C.c_int, [_P]),
     'fib_set_rect': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     'fib_set_phase': (C.c_int, [_P, _P, C.c_int, C.c_int]),
     'fib_set_table': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
@@ -188,6 +190,17 @@ class Context:
             out = np.empty((self.rows, self.width), dtype=np.float32)
         check(lib().fib_get_state(self._h, self.var(var), out.ctypes.data_as(_P), out.size))
         return out
+
+    def snapshot_begin(self, var, pinned_out):
+        """Asynchronous read of a plane into a pinned array (see pinned_empty); overlaps with the
+        steps enqueued afterwards.  snapshot_wait() completes it."""
+        if pinned_out.dtype != np.float32 or not pinned_out.flags['C_CONTIGUOUS']:
+            raise FibError('snapshot target must be a C-contiguous float32 array')
+        check(lib().fib_snapshot_begin(self._h, self.var(var), pinned_out.ctypes.data_as(_P),
+                                       pinned_out.size))
+
+    def snapshot_wait(self):
+        check(lib().fib_snapshot_wait(self._h))
 
     def get_rect(self, var, r0, r1, c0, c1):
         out = np.empty((r1 - r0, c1 - c0), dtype=np.float32)

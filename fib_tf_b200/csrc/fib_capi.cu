@@ -106,7 +106,10 @@ struct fib_ctx {
   Geom g;
   int nvars = 0, dt_per_step = 1, sms = 148;
   const char** names = nullptr;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_snap_ready = nullptr, ev_snap_done = nullptr;
+  float* snap = nullptr;              // device-side staging copy of one plane (async frame grabs)
+  bool snap_pending = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_bnd = nullptr, ev_comm = nullptr,
               ev_group = nullptr;
   float* x[2] = {nullptr, nullptr};   // diffusing variable, ping-pong, halo layout
@@ -286,6 +289,9 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   c->sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_snap_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_start));
   CU(cudaEventCreate(&c->ev_stop));
   CU(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
@@ -316,6 +322,11 @@ extern "C" int fib_destroy(fib_ctx* c) {
   DevGuard dg(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->comm_stream);
+  cudaStreamSynchronize(c->copy_stream);
+  cudaFree(c->snap);
+  cudaEventDestroy(c->ev_snap_ready);
+  cudaEventDestroy(c->ev_snap_done);
+  cudaStreamDestroy(c->copy_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
   for (int b = 0; b < 2; ++b) cudaFree(c->x[b]);
@@ -389,6 +400,34 @@ extern "C" int fib_get_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1,
   CU(cudaMemcpy2DAsync(host, (size_t)(c1 - c0) * sizeof(float), src, c->g.pitch * sizeof(float),
                        (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int fib_snapshot_begin(fib_ctx* c, int var, float* host_pinned, size_t n) {
+  if (!c || !host_pinned) return fail(FIB_E_ARG, "ctx/host is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (n != (size_t)c->g.rows * c->g.W)
+    return fail(FIB_E_ARG, "fib_snapshot_begin: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
+  DevGuard dg(c->cfg.device);
+  if (!c->snap) CU(cudaMalloc(&c->snap, c->plane_floats() * sizeof(float)));
+  if (c->snap_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_snap_done, 0));   // staging still in use
+  CU(cudaMemcpyAsync(c->snap, owned_rows(c, var), c->plane_floats() * sizeof(float),
+                     cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaEventRecord(c->ev_snap_ready, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_snap_ready, 0));
+  CU(cudaMemcpy2DAsync(host_pinned, c->g.W * sizeof(float), c->snap, c->g.pitch * sizeof(float),
+                       c->g.W * sizeof(float), c->g.rows, cudaMemcpyDeviceToHost, c->copy_stream));
+  CU(cudaEventRecord(c->ev_snap_done, c->copy_stream));
+  c->snap_pending = true;
+  return 0;
+}
+
+extern "C" int fib_snapshot_wait(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (!c->snap_pending) return 0;
+  DevGuard dg(c->cfg.device);
+  CU(cudaEventSynchronize(c->ev_snap_done));
+  c->snap_pending = false;
   return 0;
 }
 
@@ -905,6 +944,8 @@ extern "C" int fib_sync(fib_ctx* c) {
   DevGuard dg(c->cfg.device);
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->comm_stream));
+  CU(cudaStreamSynchronize(c->copy_stream));
+  c->snap_pending = false;
   return 0;
 }
 extern "C" int fib_timer_start(fib_ctx* c) {

@@ -336,6 +336,19 @@ class IonicModel:
             swx = (swx - self.min_v * sw) / (self.max_v - self.min_v)
         return swx / (self.height * self.width)
 
+    def image_async(self, pinned_out):
+        """Starts an asynchronous grab of the raw transmembrane plane of this shard into a pinned
+        array (fib_tf_b200._capi.pinned_empty) and returns at once; image_wait() completes it and
+        returns the frame normalised like image().  Lets a driver save frames (cube.npy,
+        fenton.py:179-187) without stalling the time stepping."""
+        self._ctx.snapshot_begin(self._pot_name, pinned_out)
+        self._snap = pinned_out
+
+    def image_wait(self):
+        self._ctx.snapshot_wait()
+        a = self._snap
+        return a if self.MODEL_ID == _capi.FENTON4V else self._normalise(a)
+
     def sync(self):
         self._ctx.sync()
 

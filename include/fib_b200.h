@@ -116,6 +116,14 @@ int fib_get_state(fib_ctx *ctx, int var, float *host, size_t n);
 int fib_get_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float *host);
 int fib_set_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host);
 
+/* asynchronous frame grab (the cube.npy writer of fenton.py:179-187 without stalling the stepper):
+ * fib_snapshot_begin enqueues a device-side copy of the plane (ordered after everything already
+ * enqueued) and its transfer to `host_pinned` (page-locked, rows*width floats) on a separate copy
+ * stream, then returns; later fib_step calls overlap with the transfer.  fib_snapshot_wait blocks
+ * until the host buffer is complete.  One snapshot may be in flight per context. */
+int fib_snapshot_begin(fib_ctx *ctx, int var, float *host_pinned, size_t n);
+int fib_snapshot_wait(fib_ctx *ctx);
+
 /* ---- phase field: replaces self.phi = tf.Variable(self.phase) (ionic.py:55-58) ---------
  * `rows_host` holds global rows [first_row, first_row+nrows) of the [H][W] phase field and must
  * cover this shard plus one row either side (clipped to the grid).  NULL removes the field. */

@@ -447,3 +447,23 @@ def test_courtemanche_driver_loops_stay_finite(cuda, ultra):
     q = m.calc_inter(-50.0)
     assert abs(q['m_inf'] - 0.268253) < 1e-5 and abs(q['i_NaCab'] - 102066.71) < 1.0
     m.close()
+
+
+def test_async_frame_grab_equals_synchronous_read(cuda):
+    from fib_tf_b200 import _capi
+    from fib_tf_b200.br import BeelerReuter
+    cfg = {'width': 300, 'height': 200, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.809, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': True}
+    m = BeelerReuter(cfg)
+    m.define()
+    m._ctx.step(0, 7)
+    want = m.image()
+    buf = _capi.pinned_empty((200, 300))
+    m.image_async(buf)
+    m._ctx.step(0, 9)                  # keeps stepping while the frame travels
+    got = m.image_wait()
+    assert np.array_equal(got, want)
+    m.image_async(buf)                 # staging buffer is reused safely
+    assert np.array_equal(m.image_wait(), m.image())
+    _capi.pinned_free(buf)
+    m.close()
