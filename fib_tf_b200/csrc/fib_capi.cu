@@ -545,17 +545,19 @@ extern "C" int fib_court_inter(fib_ctx* c, const float* v_host, size_t n, float*
   if (!c || !v_host || !out_host) return fail(FIB_E_ARG, "NULL argument");
   if (n == 0) return 0;
   DevGuard dg(c->cfg.device);
-  float *dv = nullptr, *dq = nullptr;
-  CU(cudaMalloc(&dv, n * sizeof(float)));
-  CU(cudaMalloc(&dq, n * kInterCols * sizeof(float)));
+  struct Tmp {
+    float* p = nullptr;
+    ~Tmp() { cudaFree(p); }
+  } tv, tq;
+  CU(cudaMalloc(&tv.p, n * sizeof(float)));
+  CU(cudaMalloc(&tq.p, n * kInterCols * sizeof(float)));
+  float *dv = tv.p, *dq = tq.p;
   CU(cudaMemcpyAsync(dv, v_host, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   court_inter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dv, (int)n, dq, kInterCols);
   CU(cudaGetLastError());
   c->launches++;
   CU(cudaMemcpyAsync(out_host, dq, n * kInterCols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  cudaFree(dv);
-  cudaFree(dq);
   return 0;
 }
 
@@ -766,7 +768,9 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
       cudaGraph_t graph = nullptr;
       CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       const uint64_t l0 = c->launches;
+      pdl_enabled() = false;               // plain kernel nodes replay faster (see fib_kernels.cuh)
       int r = run_iteration_plain(c, op);
+      pdl_enabled() = true;
       cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
       c->launches = l0;
       c->cur = cur0;

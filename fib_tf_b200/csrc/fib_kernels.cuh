@@ -41,9 +41,22 @@ struct StepArgs {
 
 constexpr int kBX = 32;   // threads along columns (one warp)
 
+// Programmatic dependent launch is used for DIRECT stream launches only (measured at 512^2, 4v:
+// direct launches 63 -> 71 Gcell-steps/s with it, CUDA-graph replay 85 -> 77, so the graph path
+// keeps plain kernel nodes).  fib_step clears this flag around stream capture.
+inline bool& pdl_enabled() {
+  static thread_local bool on = true;
+  return on;
+}
+
 template <class M, int VEC, int R, int BY, bool PHASE>
 __global__ void __launch_bounds__(kBX* BY, M::MIN_BLOCKS)
 step_kernel(const Geom g, const StepArgs<M> a) {
+  // Programmatic dependent launch: let the NEXT time step's kernel be scheduled while this one
+  // drains (its CTAs park at their own griddepcontrol.wait), and do not touch memory before the
+  // PREVIOUS step has completed and flushed.  Both are no-ops for a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   M::prologue(a);   // e.g. stage the Courtemanche LUT in shared memory
   const int c = (blockIdx.x * kBX + threadIdx.x) * VEC;
   const int strip = blockIdx.y * BY + threadIdx.y;
@@ -130,10 +143,18 @@ step_kernel(const Geom g, const StepArgs<M> a) {
 template <class M, int VEC, int R, int BY, bool PHASE>
 inline cudaError_t launch_step_r(const Geom& g, const StepArgs<M>& a, cudaStream_t st) {
   const int ncg = (g.W + VEC - 1) / VEC;
-  dim3 block(kBX, BY);
-  dim3 grid((ncg + kBX - 1) / kBX, ((a.nrows + R - 1) / R + BY - 1) / BY);
-  step_kernel<M, VEC, R, BY, PHASE><<<grid, block, M::smem_bytes(), st>>>(g, a);
-  return cudaGetLastError();
+  static const bool pdl = !(getenv("FIB_PDL") && atoi(getenv("FIB_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kBX, BY);
+  cfg.gridDim = dim3((ncg + kBX - 1) / kBX, ((a.nrows + R - 1) / R + BY - 1) / BY);
+  cfg.dynamicSmemBytes = M::smem_bytes();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, step_kernel<M, VEC, R, BY, PHASE>, g, a);
 }
 
 // Picks the marching depth R: as deep as possible while the grid still has >= 4 CTAs per SM
@@ -160,8 +181,10 @@ inline cudaError_t launch_step(const Geom& g, const StepArgs<M>& a, cudaStream_t
   if (a.nrows <= 0) return cudaSuccess;
   const bool ph = a.phase && M::NEED_LAP;
   // Small grids (<= 2^20 cells, e.g. the reference's 512^2 configs) cannot fill 148 SMs with the
-  // wide flavour: fall back to one cell per thread there (twice the CTAs, no tail wave).
-  if (M::VEC > 1 && M::VEC_SMALL != M::VEC && (long)a.nrows * g.W <= (1L << 20)) {
+  // wide flavour: fall back to one cell per thread there (twice the CTAs, no tail wave).  The
+  // choice depends on the GLOBAL grid only, so every shard and every row-range launch of a run
+  // uses the same flavour as the unsharded run.
+  if (M::VEC > 1 && M::VEC_SMALL != M::VEC && (long)g.H * g.W <= (1L << 20)) {
     if (ph) return launch_step_p<M, M::VEC_SMALL, M::BY, true>(g, a, st, sms);
     return launch_step_p<M, M::VEC_SMALL, M::BY, false>(g, a, st, sms);
   }

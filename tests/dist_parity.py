@@ -24,6 +24,7 @@ def main():
             'cheby': False, 'ultra_slow': False}
     ok = True
     for kind, extra, iters in (('fenton4v', {}, 4), ('br', {'cheby': True, 'skip': True}, 5),
+                               ('br', {'cheby': True, 'width': 1300, 'height': 900}, 3),
                                ('court', {}, 12), ('court_ultra', {'ultra_slow': True}, 8)):
         cfg = dict(base, **extra)
         models = [CLASSES[kind](dict(cfg, distributed=True, device=local))]

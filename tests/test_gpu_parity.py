@@ -127,7 +127,10 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
 
 
 @pytest.mark.parametrize('kind,extra', [('fenton4v', {}), ('br', {'cheby': True, 'skip': True}),
-                                        ('court', {}), ('court_ultra', {'ultra_slow': True})])
+                                        ('court', {}), ('court_ultra', {'ultra_slow': True}),
+                                        # > 2^20 cells: the wide kernel flavours and deeper marching
+                                        ('br', {'cheby': True, 'width': 1300, 'height': 900}),
+                                        ('fenton4v', {'width': 1100, 'height': 1000})])
 def test_row_shards_are_bit_identical_to_the_unsharded_run(cuda, kind, extra):
     """Emulates R row shards in one process (fib_step_group, device-to-device halo rows) and
     requires BIT-IDENTICAL planes: sharding must not change arithmetic; seams are interior."""
@@ -142,6 +145,7 @@ def test_row_shards_are_bit_identical_to_the_unsharded_run(cuda, kind, extra):
     whole.define()
     m = whole.m
     c0 = m._ctx
+    W0 = cfg['width']
     flags = m._flags() if hasattr(m, '_flags') else (
         (_capi.F_CHEBY if cfg['cheby'] else 0) | (_capi.F_SKIP if cfg['skip'] else 0)
         if kind == 'br' else 0)
