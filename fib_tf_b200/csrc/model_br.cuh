@@ -22,6 +22,9 @@
 #ifndef FIB_BR_MINB_SLOW
 #define FIB_BR_MINB_SLOW 6
 #endif
+#ifndef FIB_BR_MINB_SLOW_EXACT
+#define FIB_BR_MINB_SLOW_EXACT 7
+#endif
 #ifndef FIB_BR_VEC_FAST
 #define FIB_BR_VEC_FAST 2
 #endif
@@ -88,7 +91,8 @@ struct BeelerReuter {
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
-  static constexpr int MIN_BLOCKS = SLOW ? FIB_BR_MINB_SLOW : FIB_BR_MINB_FAST;
+  static constexpr int MIN_BLOCKS =
+      SLOW ? (CHEBY ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
   static constexpr bool NEED_LAP = true;
   static constexpr bool STORE_X = true;

@@ -5,15 +5,27 @@
 #pragma once
 #include "fib_kernels.cuh"
 
-// resident CTAs per SM the register allocator must leave room for, per kernel flavour (measured)
+// cells per thread / resident CTAs per SM per kernel flavour, measured on B200 (4096^2):
+//   fast op   1 cell @12 CTAs 69.6 -> 2 cells @8 CTAs 80.6 Gcell-steps/s
+//   all-state 1 cell @8 CTAs 28.4 (2 cells @3-4 CTAs: 23.8-27.5)
+//   LUT       1 cell @5 CTAs 30.0 -> 2 cells @4 CTAs 33.3
+#ifndef FIB_COURT_VEC_FAST
+#define FIB_COURT_VEC_FAST 2
+#endif
+#ifndef FIB_COURT_VEC_ALL
+#define FIB_COURT_VEC_ALL 1
+#endif
+#ifndef FIB_COURT_VEC_LUT
+#define FIB_COURT_VEC_LUT 2
+#endif
 #ifndef FIB_COURT_MINB_FAST
-#define FIB_COURT_MINB_FAST 12
+#define FIB_COURT_MINB_FAST 8
 #endif
 #ifndef FIB_COURT_MINB_ALL
 #define FIB_COURT_MINB_ALL 8
 #endif
 #ifndef FIB_COURT_MINB_LUT
-#define FIB_COURT_MINB_LUT 5
+#define FIB_COURT_MINB_LUT 4
 #endif
 
 namespace fib {
@@ -185,7 +197,8 @@ enum CourtMode {
 template <int MODE, bool LUT, bool US>
 struct Courtemanche {
   static constexpr int NS = S_COUNT;      // 21 slots; S_us only used when US
-  static constexpr int VEC = 1;
+  static constexpr int VEC =
+      MODE == COURT_FAST ? FIB_COURT_VEC_FAST : (LUT ? FIB_COURT_VEC_LUT : FIB_COURT_VEC_ALL);
   static constexpr int VEC_SMALL = 1;   // cells per thread on grids <= 2^20 cells
   static constexpr int BY = 4;
   static constexpr int MAX_R = LUT ? 2 : 1;
