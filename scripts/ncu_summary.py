@@ -70,7 +70,8 @@ if os.path.exists(lp):
             agg[r[4]][1] += float(r[-1])
     tot = sum(v[1] for v in agg.values())
     lines.append('== launch list of `python bench.py --size 4096 --steps 2 --warmup 3 --no-cpu` '
-                 '(ncu --metrics gpu__time_duration.sum, first 400 launches; shares, not absolutes)')
+                 '(ncu --metrics gpu__time_duration.sum --launch-skip 4031 --launch-count 60: the warm-up tail, the timed '
+                 'region and the e2e loop, after the 4000 launches that build the 512^2 spiral tile; shares, not absolutes)')
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append('   %5.1f %%  %4d launches  %9.1f us avg   %s' % (100 * ns / tot, n, ns / n / 1e3, k[:90]))
 open(os.path.join(OUT, '%s_ncu_summary.txt' % tag), 'w').write('\n'.join(lines) + '\n')
