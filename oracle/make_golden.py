@@ -28,6 +28,7 @@ Fixture layout (np.savez_compressed):
     meta['noise']   {'s{i}__{var}': e}: rel_err (oracle/monodomain_np.py) between two runs of the
                     unmodified reference that differ ONLY in the fp32 math library used for
                     exp/expm1/log/tanh/pow (NumPy's vs correctly rounded) -- the libm noise.
+    wide__{var}     [H,W] float64 planes of the last snapshot from the float64 run described next
     meta['rounding'] same metric between the fp32 reference and the SAME graph evaluated in float64
                     (fp32-rounded constants and inputs): the reference's total fp32 rounding error.
 """
@@ -116,7 +117,7 @@ def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=
                     model.fire_op(pname)
             if i in snaps:
                 for k, a in state_of(model, kind).items():
-                    out['s%d__%s' % (i, k)] = a.astype(np.float32)
+                    out['s%d__%s' % (i, k)] = a if _alt == 'wide' else a.astype(np.float32)
             if probe is not None:
                 trace.append(model.pot().eval()[probe[0], probe[1]])
     finally:
@@ -139,6 +140,12 @@ def run_case(name, kind, cfg, holes=(), paces=(), slow_every=0, snaps=(), probe=
                 fl = var_floor(kind, k.split('__', 1)[1])
                 noise[k] = rel_err(alt[k], out[k], fl)
                 rounding[k] = rel_err(wide[k], out[k], fl)
+        # keep the float64 planes of the LAST snapshot: lets a test ask whether another fp32
+        # implementation is as close to exact arithmetic as the reference's own fp32 run is
+        last = 's%d__' % max(snaps)
+        for k in list(out):
+            if k.startswith(last):
+                out['wide__' + k.split('__', 1)[1]] = np.asarray(wide[k], dtype=np.float64)
     meta = {
         'name': name, 'model': kind, 'config': cfg, 'holes': [list(h) for h in holes],
         'paces': [list(p) for p in paces], 'slow_every': slow_every,

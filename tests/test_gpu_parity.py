@@ -471,3 +471,29 @@ def test_async_frame_grab_equals_synchronous_read(cuda):
     assert np.array_equal(m.image_wait(), m.image())
     _capi.pinned_free(buf)
     m.close()
+
+
+@pytest.mark.parametrize('name', SHORT)
+def test_cuda_is_as_close_to_exact_arithmetic_as_the_reference(cuda, name):
+    """Independent of any tolerance on |cuda - ref|: the fixtures keep the float64 evaluation of the
+    reference graph (fp32 parameters and inputs, double arithmetic) for the last snapshot.  The
+    CUDA planes must be as close to it as the reference's own fp32 run is (factor 2.5, floor 1e-5
+    in the rel_err metric)."""
+    meta, arr = load_fixture(name)
+    last = max(meta['snaps'])
+    out = {}
+
+    def grab(i, m):
+        if i == last:
+            for v in meta['vars']:
+                out[v] = m.state[v]
+
+    m, _ = onp.run_fixture(meta, grab, model_factory=cuda.CudaModel)
+    m.close()
+    for v in meta['vars']:
+        fl = onp.var_floor(meta['model'], v)
+        truth = arr['wide__' + v]
+        e_ref = onp.rel_err(arr['s%d__%s' % (last, v)], truth, fl)
+        e_cuda = onp.rel_err(out[v], truth, fl)
+        assert e_cuda <= max(1e-5, 2.5 * e_ref), '%s %s: cuda %.2e vs reference %.2e from exact' % (
+            name, v, e_cuda, e_ref)
