@@ -46,30 +46,18 @@ class Fenton4v(IonicModel):
 
 
 if __name__ == '__main__':
-    config = {
-        'width': 512,           # screen width in pixels
-        'height': 512,          # screen height in pixels
-        'dt': 0.1,              # integration time step in ms
-        'dt_per_plot': 10,      # screen refresh interval in dt unit
-        'diff': 1.5,            # diffusion coefficient
-        'duration': 1000,       # simulation duration in ms
-        'timeline': False,      # flag to save a timeline (profiler)
-        'timeline_name': 'timeline_4v.json',
-        'save_graph': False
-    }
-    model = Fenton4v(config)
+    # the reference's driver (fenton.py:155-187): 512^2, hole, S1-S2 at 210 ms, a frame every 10 ms
+    model = Fenton4v({'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5,
+                      'duration': 1000, 'timeline': False, 'timeline_name': 'timeline_4v.json',
+                      'save_graph': False})
     model.add_hole_to_phase_field(256, 256, 30)
     model.define()
     model.add_pace_op('s2', 'luq', 1.0)
-    im = None       # headless; pass a fib_tf_b200.screen.Screen to watch
-
-    s2 = model.millisecond_to_step(210)     # 210 ms
-    ds = model.millisecond_to_step(10)
-    n = int(model.duration / 10.0)
-    cube = np.zeros([n, model.height, model.width], dtype=np.float32)
-    for i in model.run(im):
+    s2, every = model.millisecond_to_step(210), model.millisecond_to_step(10)
+    cube = np.zeros([int(model.duration / 10.0), model.height, model.width], dtype=np.float32)
+    for i in model.run(None):           # headless; pass a fib_tf_b200.screen.Screen to watch
         if i == s2:
             model.fire_op('s2')
-        if i % ds == 0:
-            cube[i // ds, :, :] = model.image() * model.phase
+        if i % every == 0:
+            cube[i // every] = model.image() * model.phase
     np.save('cube', cube)
