@@ -835,6 +835,20 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
     row += cs[i]->g.rows;
   }
   if (row != cs[0]->g.H) return fail(FIB_E_ARG, "shards cover %d of %d rows", row, cs[0]->g.H);
+  // shards on different devices of this process: direct NVLink copies need peer access
+  for (int i = 0; i + 1 < n; ++i) {
+    const int a = cs[i]->cfg.device, b = cs[i + 1]->cfg.device;
+    if (a == b) continue;
+    for (int dir = 0; dir < 2; ++dir) {
+      DevGuard dg(dir ? b : a);
+      cudaError_t e = cudaDeviceEnablePeerAccess(dir ? a : b, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();     // not fatal: cudaMemcpyPeerAsync then stages through the host
+      } else if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+      }
+    }
+  }
   const int ns = substeps_of(cs[0], op);
   if (ns == 0 || n_iter == 0) return 0;
   int r;
