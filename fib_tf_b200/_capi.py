@@ -72,6 +72,7 @@ _SIGNATURES = {
     'fib_stimulate': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
     'fib_probe': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _FP]),
     'fib_weighted_sum': (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    'fib_count_nonfinite': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     'fib_set_weights': (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),
     'fib_masked_sum': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'fib_sync': (C.c_int, [_P]),
@@ -252,6 +253,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         check(lib().fib_weighted_sum(self._h, self.var(var), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def count_nonfinite(self, var):
+        v = C.c_uint64()
+        check(lib().fib_count_nonfinite(self._h, self.var(var), C.byref(v)))
+        return int(v.value)
 
     def set_weights(self, slot, rows, first_row=0):
         a, p = _f32c(rows)

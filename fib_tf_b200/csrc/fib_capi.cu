@@ -195,6 +195,15 @@ __global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict
   if ((threadIdx.x & 31) == 0) { atomicAdd(out, sx); atomicAdd(out + 1, sw); }
 }
 
+__global__ void nonfinite_kernel(const float* __restrict__ x, Geom g, int xhalo, unsigned long long* out) {
+  unsigned long long n = 0;
+  for (int lr = blockIdx.x; lr < g.rows; lr += gridDim.x)
+    for (int c = threadIdx.x; c < g.W; c += blockDim.x)
+      n += !isfinite(x[(size_t)(lr + xhalo) * g.pitch + c]);
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
 __global__ void court_inter_kernel(const float* __restrict__ v, int n, float* __restrict__ out,
                                    int ncols) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -926,6 +935,23 @@ static int reduce_weighted(fib_ctx* c, int var, const float* w, double* sum_wx, 
   CU(cudaStreamSynchronize(c->stream));
   *sum_wx = h[0];
   *sum_w = h[1];
+  return 0;
+}
+
+extern "C" int fib_count_nonfinite(fib_ctx* c, int var, uint64_t* count) {
+  if (!c || !count) return fail(FIB_E_ARG, "ctx/count is NULL");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
+  const float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
+  nonfinite_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(
+      base, c->g, var == 0 ? 1 : 0, reinterpret_cast<unsigned long long*>(c->red));
+  CU(cudaGetLastError());
+  c->launches++;
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, c->red, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *count = h;
   return 0;
 }
 

@@ -336,6 +336,17 @@ class IonicModel:
             swx = (swx - self.min_v * sw) / (self.max_v - self.min_v)
         return swx / (self.height * self.width)
 
+    def nonfinite_cells(self):
+        """{variable: count} of NaN/Inf cells in this shard (empty dict when the state is healthy):
+        the NaN watch the reference left commented out (ionic.py:199,208-212), as one small
+        reduction per plane on the device."""
+        out = {}
+        for name in self._ctx.var_names:
+            n = self._ctx.count_nonfinite(name)
+            if n:
+                out[name] = n
+        return out
+
     def image_async(self, pinned_out):
         """Starts an asynchronous grab of the raw transmembrane plane of this shard into a pinned
         array (fib_tf_b200._capi.pinned_empty) and returns at once; image_wait() completes it and

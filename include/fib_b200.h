@@ -159,6 +159,9 @@ int fib_probe(fib_ctx *ctx, int var, int row, int col, float *out);
 /* weighted mean of a plane over this shard: sum(w*x), sum(w) (w = phase field, or 1 if none):
  * backs np.average(x, weights=phase) in court_ultra.py:466-480.  Synchronous. */
 int fib_weighted_sum(fib_ctx *ctx, int var, double *sum_wx, double *sum_w);
+/* failure detection: number of non-finite cells of a plane in this shard (the reference only has a
+ * commented-out NaN check, ionic.py:199,208-212).  Synchronous. */
+int fib_count_nonfinite(fib_ctx *ctx, int var, uint64_t *count);
 /* user weight planes (pseudo-electrogram masks, egm.py:5-12,44-47: np.mean(image * mask)):
  * fib_set_weights uploads global rows [first_row, first_row+nrows) of an [H][W] mask into `slot`
  * (0..3; must cover this shard); fib_masked_sum returns sum(mask*x) and sum(mask) over the shard. */

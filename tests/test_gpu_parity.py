@@ -470,6 +470,12 @@ def test_async_frame_grab_equals_synchronous_read(cuda):
     m.image_async(buf)                 # staging buffer is reused safely
     assert np.array_equal(m.image_wait(), m.image())
     _capi.pinned_free(buf)
+    assert m.nonfinite_cells() == {}
+    bad = m._State['M'].eval()
+    bad[5, 7] = np.nan
+    bad[9, 1] = np.inf
+    m._State['M'].assign(bad)
+    assert m.nonfinite_cells() == {'M': 2}
     m.close()
 
 
