@@ -20,10 +20,14 @@ struct Geom {
   int pitch;        // floats per row
 };
 
-// FIB_NC_LOADS=1 reads the planes through the non-coherent path (ld.global.nc).  In-place planes are
-// read exactly once, by the thread that later overwrites the same address, and L1 is invalidated at
-// every launch boundary, so no stale line can ever be observed; what it buys is freedom for the
-// scheduler to hoist the next row's loads above the current row's stores (memory-level parallelism).
+// FIB_NC_LOADS=1 (default) reads the planes through the non-coherent path (ld.global.nc).  An
+// in-place plane is read exactly once, by the thread that later overwrites the same address, and
+// L1 is invalidated at every kernel boundary, so no stale line can be observed AS LONG AS
+// consecutive step kernels do not overlap -- which is why programmatic dependent launch is compiled
+// out in this mode (fib_kernels.cuh).  It lets the scheduler interleave the state loads with the
+// phase-field / lookup-table reads: 4v + phase field 157 -> 169, Courtemanche LUT 28.5 -> 32.3
+// Gcell-steps/s; no effect on the other flavours.  FIB_NC_LOADS=0 + FIB_PDL=1 is the alternative
+// for launch-bound direct launches on tiny grids.
 #ifndef FIB_NC_LOADS
 #define FIB_NC_LOADS 1
 #endif

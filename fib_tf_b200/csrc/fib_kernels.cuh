@@ -41,9 +41,10 @@ struct StepArgs {
 
 constexpr int kBX = 32;   // threads along columns (one warp)
 
-// Programmatic dependent launch is used for DIRECT stream launches only (measured at 512^2, 4v:
-// direct launches 63 -> 71 Gcell-steps/s with it, CUDA-graph replay 85 -> 77, so the graph path
-// keeps plain kernel nodes).  fib_step clears this flag around stream capture.
+// Programmatic dependent launch (only in builds with FIB_NC_LOADS=0, see fib_common.cuh) is used
+// for DIRECT stream launches only (measured at 512^2, 4v: direct launches 63 -> 71 Gcell-steps/s
+// with it, CUDA-graph replay 85 -> 77, so the graph path keeps plain kernel nodes).  fib_step
+// clears this flag around stream capture.
 inline bool& pdl_enabled() {
   static thread_local bool on = true;
   return on;
@@ -153,7 +154,7 @@ inline cudaError_t launch_step_r(const Geom& g, const StepArgs<M>& a, cudaStream
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = (FIB_NC_LOADS == 0 && pdl && pdl_enabled()) ? 1 : 0;   // see fib_common.cuh
   return cudaLaunchKernelEx(&cfg, step_kernel<M, VEC, R, BY, PHASE>, g, a);
 }
 
