@@ -216,6 +216,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is the CPU path "with all
+    # the host threads it can use", so undo that before libgomp is loaded
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1 or 'TORCHELASTIC_RUN_ID' in os.environ:
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     tile = cpu_tile()
     val, sec, done, info = cpu_sample_run(tile, args.steps, budget_s=150.0)
     line = {
