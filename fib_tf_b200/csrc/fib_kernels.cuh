@@ -40,6 +40,9 @@ struct StepArgs {
 };
 
 constexpr int kBX = 32;   // threads along columns (one warp)
+// grids up to this many cells use VEC_SMALL cells per thread (measured crossover for BR: 512^2 -> 1 cell
+// per thread 49 vs 43 Gcell-steps/s, 640^2 -> 2 cells per thread 59 vs 53)
+constexpr long kSmallGridCells = 320L * 1024;
 
 // Programmatic dependent launch (only in builds with FIB_NC_LOADS=0, see fib_common.cuh) is used
 // for DIRECT stream launches only (measured at 512^2, 4v: direct launches 63 -> 71 Gcell-steps/s
@@ -181,11 +184,12 @@ template <class M>
 inline cudaError_t launch_step(const Geom& g, const StepArgs<M>& a, cudaStream_t st, int sms) {
   if (a.nrows <= 0) return cudaSuccess;
   const bool ph = a.phase && M::NEED_LAP;
-  // Small grids (<= 2^20 cells, e.g. the reference's 512^2 configs) cannot fill 148 SMs with the
+  // Small grids (e.g. the reference's 512^2 configs) cannot fill 148 SMs with the
   // wide flavour: fall back to one cell per thread there (twice the CTAs, no tail wave).  The
   // choice depends on the GLOBAL grid only, so every shard and every row-range launch of a run
   // uses the same flavour as the unsharded run.
-  if (M::VEC > 1 && M::VEC_SMALL != M::VEC && (long)g.H * g.W <= (1L << 20)) {
+  static const long small_cells = getenv("FIB_SMALL_CELLS") ? atol(getenv("FIB_SMALL_CELLS")) : kSmallGridCells;
+  if (M::VEC > 1 && M::VEC_SMALL != M::VEC && (long)g.H * g.W <= small_cells) {
     if (ph) return launch_step_p<M, M::VEC_SMALL, M::BY, true>(g, a, st, sms);
     return launch_step_p<M, M::VEC_SMALL, M::BY, false>(g, a, st, sms);
   }

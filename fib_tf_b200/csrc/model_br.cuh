@@ -87,7 +87,7 @@ template <bool CHEBY, bool SLOW>
 struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
   static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
-  static constexpr int VEC_SMALL = 1;   // cells per thread on grids <= 2^20 cells
+  static constexpr int VEC_SMALL = 1;   // cells per thread on small grids (kSmallGridCells)
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)

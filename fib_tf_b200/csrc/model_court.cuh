@@ -199,7 +199,7 @@ struct Courtemanche {
   static constexpr int NS = S_COUNT;      // 21 slots; S_us only used when US
   static constexpr int VEC =
       MODE == COURT_FAST ? FIB_COURT_VEC_FAST : (LUT ? FIB_COURT_VEC_LUT : FIB_COURT_VEC_ALL);
-  static constexpr int VEC_SMALL = 1;   // cells per thread on grids <= 2^20 cells
+  static constexpr int VEC_SMALL = 1;   // cells per thread on small grids (kSmallGridCells)
   static constexpr int BY = 4;
   static constexpr int MAX_R = LUT ? 2 : 1;
   static constexpr int AUTO_R = LUT ? 2 : 1;   // marching depth picked by launch_step (measured best)

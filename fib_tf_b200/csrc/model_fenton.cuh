@@ -12,7 +12,7 @@ namespace fib {
 struct Fenton4v {
   static constexpr int NS = 3;            // V, W, S  (U is the diffusing variable)
   static constexpr int VEC = 4;
-  static constexpr int VEC_SMALL = 4;   // cells per thread on grids <= 2^20 cells
+  static constexpr int VEC_SMALL = 4;   // cells per thread on small grids (kSmallGridCells)
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 4;   // marching depth picked by launch_step (measured best)

@@ -128,7 +128,7 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
 
 @pytest.mark.parametrize('kind,extra', [('fenton4v', {}), ('br', {'cheby': True, 'skip': True}),
                                         ('court', {}), ('court_ultra', {'ultra_slow': True}),
-                                        # > 2^20 cells: the wide kernel flavours and deeper marching
+                                        # large enough for the wide kernel flavours and deeper marching
                                         ('br', {'cheby': True, 'width': 1300, 'height': 900}),
                                         ('fenton4v', {'width': 1100, 'height': 1000})])
 def test_row_shards_are_bit_identical_to_the_unsharded_run(cuda, kind, extra):
