@@ -49,6 +49,7 @@ def _cfg(**kw):
     (dict(dt=0.0), 'dt must be'),
     (dict(steps_per_launch=3), 'steps_per_launch'),
     (dict(row0=10, rows=10), 'outside the grid'),
+    (dict(height=70000, width=40000), '2^31'),      # 32-bit element offsets: shard the grid instead
 ])
 def test_create_rejects_bad_arguments(kw, needle):
     L = _capi.lib()

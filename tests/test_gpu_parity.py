@@ -214,6 +214,29 @@ def test_planar_wave_property_at_4096(cuda):
     gpu.close()
 
 
+def test_planar_wave_property_at_the_bench_size_32768(cuda):
+    """The same property at the size the bench line is quoted on (32768^2, 20 GiB of state): rows
+    sampled across the grid are identical to each other and match the oracle's 5-row strip."""
+    N = 32768
+    cfg = {'width': N, 'height': N, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False}
+    gpu = cuda.CudaModel('fenton4v', cfg)
+    gpu.define()
+    ref = onp.OracleModel('fenton4v', dict(cfg, height=5))
+    ref.define()
+    for _ in range(2):
+        gpu.iterate()
+        ref.iterate()
+    ctx = gpu.m._ctx
+    for v in ('U', 'V', 'W', 'S'):
+        rows = [ctx.get_rect(v, r, r + 1, 0, N)[0] for r in (0, 1, 2, 4097, 16384, N - 2, N - 1)]
+        for a in rows[1:]:
+            assert np.array_equal(a, rows[0]), v
+        assert onp.rel_err(rows[0], ref.state[v][2], 1e-3) <= 1e-5, v
+    assert gpu.m.nonfinite_cells() == {}
+    gpu.close()
+
+
 def test_uniform_rest_state_stays_uniform_at_4096(cuda):
     """A uniform field has a Laplacian of exactly 0 in fp32 (4c + 2c - 6c), so a uniform BR state
     must stay exactly uniform at any size."""
