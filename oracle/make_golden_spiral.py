@@ -9,6 +9,7 @@ S2 'luq' at 210 ms, 1000 ms) and br.py:347-382 (BR 512^2, cheby=True, hole (150,
 
     python oracle/make_golden_spiral.py fenton      -> tests/golden/spiral_fenton.npz
     python oracle/make_golden_spiral.py br          -> tests/golden/spiral_br.npz
+    python oracle/make_golden_spiral.py court | court_ultra   (700 ms, court.py / court_ultra.py loops)
 
 Stored: the transmembrane variable at PROBES after every run() iteration ([samples, n_probes] fp32)
 and 64x64 block-subsampled frames every 50 ms -- enough to compare rotation period, APD and
@@ -43,14 +44,28 @@ def main(which):
                'timeline': False, 'timeline_name': 'unused.json', 'save_graph': False}
         model = fenton.Fenton4v(cfg)
         hole, s2_ms, s2_v = (256, 256, 30), 210, 1.0
-    else:
+    elif which == 'br':
         import br
         cfg = {'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.809, 'duration': 1000,
                'skip': False, 'cheby': True, 'timeline': False, 'timeline_name': 'unused.json',
                'save_graph': False}
         model = br.BeelerReuter(cfg)
         hole, s2_ms, s2_v = (150, 200, 40), 300, 10.0
+    else:
+        # court.py:582-621 / court_ultra.py:489-512 driver loops (holes, S2 'luq' = 10 mV, 'slow'
+        # fired every 10th iteration), shortened to 700 ms
+        import court
+        import court_ultra
+        ultra = which == 'court_ultra'
+        cfg = {'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5 if ultra else 0.809,
+               'duration': 700, 'skip': False, 'cheby': True, 'timeline': False,
+               'timeline_name': 'unused.json', 'save_graph': False, 'ultra_slow': False}
+        model = (court_ultra if ultra else court).Courtemanche(cfg)
+        hole, s2_ms, s2_v = ((256, 256, 10) if ultra else (256, 256, 30)), (300 if ultra else 350), 10.0
+        extra_hole = (256, 256, 250, True)
     model.add_hole_to_phase_field(*hole)
+    if which.startswith('court'):
+        model.add_hole_to_phase_field(*extra_hole)
     model.define()
     model.add_pace_op('s2', 'luq', s2_v)
     s2 = model.millisecond_to_step(s2_ms)
@@ -61,6 +76,8 @@ def main(which):
     sys.stdout = open(os.devnull, 'w')
     try:
         for i in model.run(None):
+            if which.startswith('court') and i % 10 == 0:
+                model.fire_op('slow')
             if i == s2:
                 model.fire_op('s2')
             x = model.pot().eval()
@@ -72,7 +89,7 @@ def main(which):
     finally:
         sys.stdout.close()
         sys.stdout = out_stream
-    meta = {'model': which, 'config': cfg, 'hole': hole, 's2_ms': s2_ms, 's2_value': s2_v, 's2_iter': s2,
+    meta = {'model': which, 'config': cfg, 'hole': hole, 'extra_hole': extra_hole if which.startswith('court') else None, 's2_ms': s2_ms, 's2_value': s2_v, 's2_iter': s2,
             'dt_per_step': model.dt_per_step, 'probes': PROBES, 'frame_every_iter': every,
             'generator': 'oracle/make_golden_spiral.py (unmodified reference under oracle/tfshim.py)',
             'seconds': time.time() - t0}
