@@ -30,3 +30,26 @@ def test_oracle_reproduces_reference_bitwise(name):
     assert seen == meta['snaps']
     if meta['probe']:
         assert np.array_equal(trace, arr['probe'])
+
+
+@pytest.mark.parametrize('which,kind,iters', [('fenton', 'fenton4v', 4), ('br', 'br', 6),
+                                             ('court', 'court', 21), ('court_ultra', 'court_ultra', 12)])
+def test_oracle_reproduces_the_start_of_the_512_driver_runs_bitwise(which, kind, iters):
+    """The first iterations of the 512^2 driver runs stored by oracle/make_golden_spiral.py (the
+    unmodified reference) against the oracle: bit-identical probe values."""
+    import json
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'spiral_%s.npz' % which))
+    meta = json.loads(str(z['meta']))
+    m = onp.OracleModel(kind, meta['config'])
+    m.add_hole(*meta['hole'])
+    if meta.get('extra_hole'):
+        m.add_hole(*meta['extra_hole'])
+    m.define()
+    for i in range(iters):
+        m.iterate()
+        if kind.startswith('court') and i % 10 == 0:
+            m.fire('slow')
+        got = np.array([m.pot()[r, c] for r, c in meta['probes']], np.float32)
+        assert np.array_equal(got, z['probes'][i]), (which, i)
