@@ -107,3 +107,34 @@ def test_spiral_run_matches_the_reference_statistically(cuda_device, which):
     assert np.max(np.abs(frames[:n_pre] - ref_frames[:n_pre])) <= 0.01 * (hi - lo) * 5
     for f_c, f_r in zip(frames[n_pre + 2:], ref_frames[n_pre + 2:]):
         assert abs((f_c > level).mean() - (f_r > level).mean()) <= 0.05
+
+
+def test_lookup_table_flavour_tracks_the_exact_model(cuda_device):
+    """The 150x30 table with its truncating 1-mV lookup (courtemanche.h:354-357) is an APPROXIMATION
+    of calc_inter; this quantifies it on the court_ultra.py driver run: against the exact reference,
+    every activation time within 3 % + 2 ms and every APD within 15 % (measured: <= 1.1 % on times,
+    1-11 % on APD -- the truncation shortens the short, high-rate action potentials most)."""
+    from fib_tf_b200.court_ultra import Courtemanche
+    meta, ref_probes, _ = load('court_ultra')
+    model = Courtemanche(dict(meta['config'], lut=True))
+    model.add_hole_to_phase_field(*meta['hole'])
+    model.add_hole_to_phase_field(*meta['extra_hole'])
+    model.define()
+    model.add_pace_op('s2', 'luq', meta['s2_value'])
+    probes = []
+    for i in model.run(None):
+        if i == meta['s2_iter']:
+            model.fire_op('s2')
+        probes.append([model._ctx.probe('V', r, c) for r, c in meta['probes']])
+    probes = np.asarray(probes, np.float32)
+    model.close()
+    dt_iter, compared = meta['config']['dt'], 0
+    for k in range(probes.shape[1]):
+        up_r, dn_r = events(ref_probes[:, k], -25.0, dt_iter)
+        up_c, dn_c = events(probes[:, k], -25.0, dt_iter)
+        if len(up_r) == len(up_c) and len(up_r) >= 2:
+            assert np.all(np.abs(up_c - up_r) <= 0.03 * up_r + 2.0), (k, up_c, up_r)
+            a_r, a_c = apds(up_r, dn_r), apds(up_c, dn_c)
+            assert len(a_r) == len(a_c) and np.all(np.abs(a_c - a_r) <= 0.15 * a_r + 1.0), (k, a_c, a_r)
+            compared += 1
+    assert compared >= 4
