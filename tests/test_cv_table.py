@@ -24,7 +24,7 @@ def test_oracle_reproduces_published_cv_4v():
     got = {d: oracle_cv('fenton4v', d) for d in (0.4, 0.8, 1.0, 1.5)}
     dx, worst = cv.fit_dx(got, cv.CV_TABLE_4V)
     assert abs(dx - 0.0302) < 0.0004, dx
-    assert worst < 0.015, (dx, worst, got)
+    assert worst < 0.01, (dx, worst, got)
 
 
 def test_oracle_reproduces_published_cv_br():
@@ -54,9 +54,11 @@ def test_cuda_reproduces_published_cv_table(cuda_device, kind, table, flags):
                                   lambda mm: mm.m._ctx.get_rect(mm.m._pot_name, 2, 3, 0, width)[0])
         m.close()
     dx, worst = cv.fit_dx(got, table)
-    # the published BR column is itself only self-consistent to ~1.5 % under ONE grid spacing
-    # (SURVEY.md Appendix B.1); cheby=True is another 0.6-2 % slower than the exact gates
-    tol = 0.015 if kind == 'fenton4v' else (0.02 if not flags else 0.035)
+    # 4v: the north-star 1 % bar (measured worst residual 0.34 %).  The published BR column is itself
+    # only self-consistent to ~1.5 % under ONE grid spacing (the CPU oracle
+    # has the same 1.5 % residual) and cheby=True is another 0.6-2 % slower than the exact gates; the
+    # 1 % CUDA-vs-reference bar for BR is test_cuda_cv_matches_oracle_within_1_percent below.
+    tol = 0.01 if kind == 'fenton4v' else (0.02 if not flags else 0.035)
     assert 0.0290 < dx < 0.0312, dx
     assert worst < tol, (dx, worst, got)
 
