@@ -73,14 +73,14 @@ __device__ __forceinline__ float clip_tf(float x, float lo, float hi) {
 // IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).
 // neg_dt = fp32(-dt) (or fp32(-(dt*n)) folded in double on the host, br.py:197-200).
 __device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, float neg_dt) {
-  float e = m_expm1(m_div(neg_dt, tau));
+  float e = m_expm1_neg(m_div(neg_dt, tau));
   return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 // Rush-Larsen with caller-supplied clip bounds: (1e-5, 0.99999) for the Python models, (-inf, +inf)
 // for the native courtemanche.h rule, which does not clip (courtemanche.h:287-292)
 __device__ __forceinline__ float rush_larsen_b(float g, float g_inf, float tau, float neg_dt, float lo,
                                                float hi) {
-  const float e = m_expm1(m_div(neg_dt, tau));
+  const float e = m_expm1_neg(m_div(neg_dt, tau));
   const float r = fmaf(g - g_inf, e, g);
   return lo == -INFINITY ? r : clip_tf(r, lo, hi);      // uniform select; no clip in native mode
 }

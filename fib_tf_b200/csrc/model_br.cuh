@@ -70,7 +70,97 @@ __device__ __forceinline__ void br_inf_rate_exact(float v, float& inf, float& ra
 
 // rush_larsen with tau given as its reciprocal: expm1(-dt/tau) = expm1(-dt * rate)
 __device__ __forceinline__ float rush_larsen_rate(float g, float g_inf, float rate, float neg_dt) {
-  return rush_larsen_e(g, g_inf, m_expm1(neg_dt * rate));
+  return rush_larsen_e(g, g_inf, m_expm1_neg(neg_dt * rate));
+}
+
+// a = n1/d1, b = n2/d2 (all four positive): rate = a + b = (n1 d2 + n2 d1)/(d1 d2) and
+// inf = a/rate = n1 d2/(n1 d2 + n2 d1) -- two SFU reciprocals instead of three, no cancellation.
+__device__ __forceinline__ float rush_larsen_frac(float g, float n1, float d1, float n2, float d2,
+                                                  float neg_dt) {
+  const float n1d2 = n1 * d2;
+  const float N = fmaf(n2, d1, n1d2);
+  const float rate = N * m_rcp(d1 * d2);
+  return rush_larsen_rate(g, n1d2 * m_rcp(N), rate, neg_dt);
+}
+
+// The exact gates of br.py:175-205 / 255-273 for one cell, same formulas as br_inf_rate_exact
+// (which stays as the readable statement and is what tests/test_gpu_parity.py's accurate-math
+// build checks), with the SFU work trimmed -- the exact-gate kernel is MUFU-bound (~47 SFU ops per
+// cell): exponentials that differ only by a constant factor are computed once
+//   e^{-0.25(v+78)} = e^{-0.25(v+77)} e^{-0.25}          (alpha_j <- alpha_h)
+//   e^{-0.2(v+30)}  = e^{-0.2(v+78)} e^{9.6}              (beta_f  <- alpha_j)
+//   e^{-0.1(v+32)}  = e^{-0.1(v+47)} e^{1.5}              (beta_j  <- alpha_m)
+//   e^{-0.04(v+20)} = e^{-0.8} / e^{0.04 v}                (beta_xi <- the currents' k)
+// and the two-fraction gates use rush_larsen_frac.  m and h keep the reference's operation
+// structure, so V0 == -47.0f still yields the reference's 0/0 -> clip upper bound (fib_common.cuh).
+template <bool SLOW>
+__device__ __forceinline__ void br_gates_exact(float v, float rk, float (&s)[7], float neg_dt,
+                                               float neg_dt_slow) {
+#if FIB_ACCURATE_MATH
+  float inf, rate;
+  br_inf_rate_exact<1>(v, inf, rate); s[1] = rush_larsen_rate(s[1], inf, rate, neg_dt);
+  br_inf_rate_exact<2>(v, inf, rate); s[2] = rush_larsen_rate(s[2], inf, rate, neg_dt);
+  if (SLOW) {
+    br_inf_rate_exact<0>(v, inf, rate); s[6] = rush_larsen_rate(s[6], inf, rate, neg_dt_slow);
+    br_inf_rate_exact<3>(v, inf, rate); s[3] = rush_larsen_rate(s[3], inf, rate, neg_dt_slow);
+    br_inf_rate_exact<4>(v, inf, rate); s[4] = rush_larsen_rate(s[4], inf, rate, neg_dt_slow);
+    br_inf_rate_exact<5>(v, inf, rate); s[5] = rush_larsen_rate(s[5], inf, rate, neg_dt_slow);
+  }
+  (void)rk;
+#else
+  // m: a = -(v+47)/expm1(-0.1(v+47)), b = 40 e^{-0.056(v+72)}
+  const float zm = -0.1f * (v + 47.f);
+  const float E10 = m_exp(zm);
+  {
+    float q = 1.38888888888889e-3f;                // m_expm1(zm) with its exponential kept
+    q = fmaf(q, zm, 8.33333333333333e-3f);
+    q = fmaf(q, zm, 4.16666666666667e-2f);
+    q = fmaf(q, zm, 1.66666666666667e-1f);
+    q = fmaf(q, zm, 0.5f);
+    q = fmaf(q * zm, zm, zm);
+    const float den = fabsf(zm) < 0.125f ? q : E10 - 1.0f;
+    const float a = m_div(-1.f * (v + 47.f), den);
+    const float b = m_exp_affine(-0.056f * (v + 72.f), 40.f, 0.f);
+    const float rate = a + b;
+    s[1] = rush_larsen_rate(s[1], m_div(a, rate), rate, neg_dt);
+  }
+  // h: a = 0.126 e^{-0.25(v+77)}, b = 1.7/(e^{-0.082(v+22.5)} + 1)
+  const float E25 = m_exp(-.25f * (v + 77.f));
+  {
+    const float a = 0.126f * E25;
+    const float b = m_div(1.7f, m_exp_affine(-0.082f * (v + 22.5f), 1.f, 1.f));
+    const float rate = a + b;
+    s[2] = rush_larsen_rate(s[2], m_div(a, rate), rate, neg_dt);
+  }
+  if (SLOW) {
+    // j: a = 0.055 e^{-0.25(v+78)}/(e^{-0.2(v+78)} + 1), b = 0.3/(e^{-0.1(v+32)} + 1)
+    const float E20 = m_exp(-0.2f * (v + 78.f));
+    s[3] = rush_larsen_frac(s[3], E25 * (0.055f * 0.7788007830714049f), E20 + 1.f, 0.3f,
+                            fmaf(E10, 4.4816890703380645f, 1.f), neg_dt_slow);
+    // d (rates doubled, br.py:46-48): a = 0.19 e^{-0.01(v-5)}/(e^{-0.072(v-5)} + 1),
+    //                                 b = 0.14 e^{-0.017(v+44)}/(e^{0.05(v+44)} + 1)
+    s[4] = rush_larsen_frac(s[4], m_exp_affine(-0.01f * (v - 5.f), (float)(2 * 0.095), 0.f),
+                            m_exp_affine(-0.072f * (v - 5.f), 1.f, 1.f),
+                            m_exp_affine(-0.017f * (v + 44.f), (float)(2 * 0.07), 0.f),
+                            m_exp_affine(0.05f * (v + 44.f), 1.f, 1.f), neg_dt_slow);
+    // f (doubled): a = 0.024 e^{-0.008(v+28)}/(e^{0.15(v+28)} + 1),
+    //              b = 0.013 e^{-0.02(v+30)}/(e^{-0.2(v+30)} + 1)
+    s[5] = rush_larsen_frac(s[5], m_exp_affine(-0.008f * (v + 28.f), (float)(2 * 0.012), 0.f),
+                            m_exp_affine(0.15f * (v + 28.f), 1.f, 1.f),
+                            m_exp_affine(-0.02f * (v + 30.f), (float)(2 * 0.0065), 0.f),
+                            fmaf(E20, 14764.781565577266f, 1.f), neg_dt_slow);
+    // xi: a = 0.0005 e^{0.083(v+50)}/(e^{0.057(v+50)} + 1), b = 0.0013 e^{-0.06(v+20)}/(e^{-0.04(v+20)} + 1)
+    s[6] = rush_larsen_frac(s[6], m_exp_affine(0.083f * (v + 50.f), 0.0005f, 0.f),
+                            m_exp_affine(0.057f * (v + 50.f), 1.f, 1.f),
+                            m_exp_affine(-0.06f * (v + 20.f), 0.0013f, 0.f),
+                            fmaf(rk, 0.44932896411722156f, 1.f), neg_dt_slow);
+  }
+#endif
+}
+// rush_larsen with the argument-compensated expm1 (same result class, three instructions longer)
+__device__ __forceinline__ float rush_larsen_comp(float g, float g_inf, float tau, float neg_dt) {
+  float e = m_expm1(m_div(neg_dt, tau));
+  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 // Horner evaluation of c0 + c1 x + ... + c8 x^8.  Every FMA has exactly ONE constant-bank operand
 // (the coefficient lives in the kernel parameter bank), so no LDC is needed; Estrin's scheme was
@@ -112,14 +202,22 @@ struct BeelerReuter {
                                               float V0, float lap, float (&s)[NS], float& Vnew) {
     const Params& p = a.p;
     const float C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
+    // every current exponential is k = e^{0.04 V0} times a constant; the exact gates reuse 1/k.
+    // (The polynomial flavour computes k AFTER its gates: hoisting it costs that kernel 10 %.)
+    float k, rk;
 
     if (CHEBY) {
       // x = (V0 - 0.5(max+min)) / (0.5(max-min)) = (V0 + 30)/60   (br.py:215)
       const float x = (V0 + 30.0f) * (1.0f / 60.0f);
 #define FIB_BR_GATE(RL, g, idx, ndt) \
   s[idx] = RL(s[idx], br_poly8(p.poly[2 * (g)], x), br_poly8(p.poly[2 * (g) + 1], x), ndt)
-      FIB_BR_GATE(rush_larsen, 1, 1, p.neg_dt);                 // m
-      FIB_BR_GATE(rush_larsen, 2, 2, p.neg_dt);                 // h
+      if (SLOW) {
+        FIB_BR_GATE(rush_larsen, 1, 1, p.neg_dt);                 // m
+        FIB_BR_GATE(rush_larsen, 2, 2, p.neg_dt);                 // h
+      } else {   // the HBM-bound two-gate step schedules better around the longer expm1 (114 -> 118)
+        FIB_BR_GATE(rush_larsen_comp, 1, 1, p.neg_dt);            // m
+        FIB_BR_GATE(rush_larsen_comp, 2, 2, p.neg_dt);            // h
+      }
       if (SLOW) {
         FIB_BR_GATE(rush_larsen, 0, 6, p.neg_dt_slow);         // xi
         FIB_BR_GATE(rush_larsen, 3, 3, p.neg_dt_slow);         // j
@@ -127,16 +225,12 @@ struct BeelerReuter {
         FIB_BR_GATE(rush_larsen, 5, 5, p.neg_dt_slow);         // f
       }
 #undef FIB_BR_GATE
+      k = m_exp(0.04f * V0);
+      rk = m_rcp(k);
     } else {
-      float inf, rate;
-      br_inf_rate_exact<1>(V0, inf, rate); s[1] = rush_larsen_rate(M, inf, rate, p.neg_dt);
-      br_inf_rate_exact<2>(V0, inf, rate); s[2] = rush_larsen_rate(H, inf, rate, p.neg_dt);
-      if (SLOW) {
-        br_inf_rate_exact<0>(V0, inf, rate); s[6] = rush_larsen_rate(XI, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<3>(V0, inf, rate); s[3] = rush_larsen_rate(J, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<4>(V0, inf, rate); s[4] = rush_larsen_rate(D, inf, rate, p.neg_dt_slow);
-        br_inf_rate_exact<5>(V0, inf, rate); s[5] = rush_larsen_rate(F, inf, rate, p.neg_dt_slow);
-      }
+      k = m_exp(0.04f * V0);
+      rk = m_rcp(k);
+      br_gates_exact<SLOW>(V0, rk, s, p.neg_dt, p.neg_dt_slow);
     }
 
     // currents from V0 and the OLD gates (br.py:150-165); k = e^{0.04 V0}
@@ -144,14 +238,13 @@ struct BeelerReuter {
     constexpr float E53 = 8.331137487687693f;     // e^{0.04*53}
     constexpr float E77 = 21.75840239619708f;    // e^{0.04*77}
     constexpr float E35 = 4.055199966844675f;    // e^{0.04*35}
-    const float k = m_exp(0.04f * V0);
     const float k53 = k * E53;
     const float d23 = V0 + 23.0f;
     // (V0+23) / (1 - e^{-0.04 (V0+23)}): removable singularity at -23 mV.  Away from it
     // 1 - e^{-0.92}/k is accurate and free (k is already known); within +-3 mV the expm1
     // polynomial takes over.
     constexpr float E23N = 0.3985190410845142f;   // e^{-0.04*23}
-    float one_m_e = fmaf(-E23N, m_rcp(k), 1.0f);
+    float one_m_e = fmaf(-E23N, rk, 1.0f);
     {
       const float z = -0.04f * d23;               // |z| < 0.125 <=> within 3.1 mV of the singularity
       float q = 1.38888888888889e-3f;
@@ -164,7 +257,10 @@ struct BeelerReuter {
     }
     const float sing = m_div(d23, one_m_e);
     const float iK1 = 0.35f * (m_div(4.f * fmaf(k, E85, -1.f), fmaf(k53, k53, k53)) + 0.2f * sing);
-    const float ix1 = XI * 0.8f * m_div(fmaf(k, E77, -1.f), k * E35);
+        // measured: reusing 1/k is +3 % for the six-gate polynomial step, -1.5 % for its two-gate one
+    const float ix1 = (SLOW || !CHEBY)
+                          ? XI * 0.8f * (fmaf(k, E77, -1.f) * (rk * (1.0f / E35)))
+                          : XI * 0.8f * m_div(fmaf(k, E77, -1.f), k * E35);
     const float iNa = (4.0f * M * M * M * H * J + 0.005f) * (V0 - 50.0f);
     const float ECa = -82.3f - 13.0278f * m_log(C);
     const float iCa = 0.09f * D * F * (V0 - ECa);
