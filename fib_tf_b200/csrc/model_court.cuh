@@ -65,7 +65,15 @@ constexpr double V_i = V_cell * 0.68, V_rel = 0.0048 * V_cell, V_up = 0.0552 * V
 
 // calc_inter (court.py:273-429): the V-only intermediates.  eps = V*1e-20 is the reference's
 // broadcast trick (court.py:299); it is kept where it is observable (alpha_h, alpha_j).
-template <bool WANT_US>
+//
+// RATES = false is the reference's table: the Q_tau_* columns hold time constants (the lookup
+// table, fib_court_inter).  RATES = true is what the direct (no-table) kernels use: the Q_tau_*
+// slots hold 1/tau instead, because the only consumer is expm1(-dt/tau) and every tau here is
+// itself 1/(alpha + beta): forming tau and dividing by it again costs two SFU reciprocals per gate
+// for nothing.  Where alpha and beta are both fractions the sum goes over the common denominator
+// (one reciprocal).  Same formulas in real arithmetic, ~22 of ~130 SFU operations per cell fewer;
+// the all-state kernel is SFU-bound (profiles/r1_ncu_summary.txt: xu pipe 75 %).
+template <bool WANT_US, bool RATES = false>
 __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols]) {
   using namespace cc;
   const float eps = V * 1e-20f;
@@ -73,9 +81,14 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
   {
     const float w = V + 10.0001f;
     const float e = m_exp(w * -FIB_RCPF(6.24));
-    q[Q_tau_d] = fabsf(w) < 1.0e-10f
-                     ? 4.579f / (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24)))
-                     : m_div(1.0f - e, 0.0350000f * w * (1.0f + e));
+    if (RATES)
+      q[Q_tau_d] = fabsf(w) < 1.0e-10f
+                       ? (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24))) / 4.579f
+                       : m_div(0.0350000f * w * (1.0f + e), 1.0f - e);
+    else
+      q[Q_tau_d] = fabsf(w) < 1.0e-10f
+                       ? 4.579f / (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24)))
+                       : m_div(1.0f - e, 0.0350000f * w * (1.0f + e));
   }
   {
     const float e = m_exp(-(V + 28.0f) * FIB_RCPF(6.9));
@@ -83,13 +96,18 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
   }
   {
     const float a = (V + 10.0f);
-    q[Q_tau_f] = 9.0f * m_rcp(0.0197000f * m_exp(-(0.0337f * 0.0337f) * (a * a)) + 0.02f);
+    const float x = 0.0197000f * m_exp(-(0.0337f * 0.0337f) * (a * a)) + 0.02f;
+    q[Q_tau_f] = RATES ? x * FIB_RCPF(9.0) : 9.0f * m_rcp(x);
   }
   {
     const float w = V - 7.9f;
     const float e = m_exp(-w * 0.2f);
-    q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)((6.0 * 0.2) / 1.3)
-                                     : m_div(6.0f * (1.0f - e), (1.0f + 0.3f * e) * 1.0f * w);
+    if (RATES)
+      q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)(1.3 / (6.0 * 0.2))
+                                       : m_div((1.0f + 0.3f * e) * 1.0f * w, 6.0f * (1.0f - e));
+    else
+      q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)((6.0 * 0.2) / 1.3)
+                                       : m_div(6.0f * (1.0f - e), (1.0f + 0.3f * e) * 1.0f * w);
   }
   q[Q_w_inf] = 1.0f - m_rcp(1.0f + m_exp(-(V - 40.0f) * FIB_RCPF(17.0)));
   {
@@ -99,7 +117,7 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
     const float beta_m = 0.08f * m_exp(-V * FIB_RCPF(11.0));
     const float r = m_rcp(alpha_m + beta_m);
     q[Q_m_inf] = alpha_m * r;
-    q[Q_tau_m] = r;
+    q[Q_tau_m] = RATES ? alpha_m + beta_m : r;
   }
   const bool lo = V < -40.0f;
   {
@@ -108,9 +126,20 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
                             : m_rcp(0.13f * (1.0f + m_exp((V + 10.66f) * -FIB_RCPF(11.1))));
     const float r = m_rcp(alpha_h + beta_h);
     q[Q_h_inf] = alpha_h * r;
-    q[Q_tau_h] = r;
+    q[Q_tau_h] = RATES ? alpha_h + beta_h : r;
   }
-  {
+  if (RATES) {
+    // alpha_j = aN/aD, beta_j = bN/bD over the common denominator (branch selects as below)
+    const float aN = lo ? (-127140.f * m_exp(0.2444f * V) - 3.474e-05f * m_exp(-0.04391f * V)) * (V + 37.78f)
+                        : eps;
+    const float aD = lo ? 1.0f + m_exp(0.311f * (V + 79.23f)) : 1.0f;
+    const float bN = lo ? 0.1212f * m_exp(-0.01052f * V) : 0.3f * m_exp(-2.535e-07f * V);
+    const float bD = lo ? 1.0f + m_exp(-0.1378f * (V + 40.14f)) : 1.0f + m_exp(-0.1f * (V + 32.0f));
+    const float x = aN * bD;
+    const float t = fmaf(bN, aD, x);
+    q[Q_j_inf] = x * m_rcp(t);
+    q[Q_tau_j] = t * m_rcp(aD * bD);
+  } else {
     const float alpha_j =
         lo ? m_div((-127140.f * m_exp(0.2444f * V) - 3.474e-05f * m_exp(-0.04391f * V)) * (V + 37.78f),
                    1.0f + m_exp(0.311f * (V + 79.23f)))
@@ -124,42 +153,52 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
   const float Vs = V - -10.0f;
   {
     // alpha/beta of oa and ua are the same expressions (court.py:363-364, 375-376)
-    const float alpha = 0.65f * m_rcp(m_exp(Vs * -FIB_RCPF(8.5)) + m_exp((Vs - 40.0f) * -FIB_RCPF(59.0)));
-    const float beta = 0.65f * m_rcp(2.5f + m_exp((Vs + 72.0f) * FIB_RCPF(17.0)));
-    const float t = m_rcp(alpha + beta) * FIB_RCPF(3.0);
+    const float x = m_exp(Vs * -FIB_RCPF(8.5)) + m_exp((Vs - 40.0f) * -FIB_RCPF(59.0));
+    const float y = 2.5f + m_exp((Vs + 72.0f) * FIB_RCPF(17.0));
+    float t;
+    if (RATES) {      // K_Q10 (0.65/x + 0.65/y) = 1.95 (x + y)/(x y)
+      t = ((float)(3.0 * 0.65) * (x + y)) * m_rcp(x * y);
+    } else {
+      const float alpha = 0.65f * m_rcp(x);
+      const float beta = 0.65f * m_rcp(y);
+      t = m_rcp(alpha + beta) * FIB_RCPF(3.0);
+    }
     q[Q_tau_oa] = t;
     q[Q_tau_ua] = t;
   }
   q[Q_oa_inf] = m_rcp(1.0f + m_exp((Vs + 10.47f) * -FIB_RCPF(17.54)));
   {
-    const float alpha = m_rcp(18.53f + 1.0f * m_exp((Vs + 103.7f) * FIB_RCPF(10.95)));
-    const float beta = m_rcp(35.56f + 1.0f * m_exp((Vs - 8.74f) * -FIB_RCPF(7.44)));
-    q[Q_tau_oi] = m_rcp(alpha + beta) * FIB_RCPF(3.0);
+    const float x = 18.53f + 1.0f * m_exp((Vs + 103.7f) * FIB_RCPF(10.95));
+    const float y = 35.56f + 1.0f * m_exp((Vs - 8.74f) * -FIB_RCPF(7.44));
+    if (RATES) q[Q_tau_oi] = (3.0f * (x + y)) * m_rcp(x * y);
+    else q[Q_tau_oi] = m_rcp(m_rcp(x) + m_rcp(y)) * FIB_RCPF(3.0);
   }
   q[Q_oi_inf] = m_rcp(1.0f + m_exp((Vs + 33.1f) * FIB_RCPF(5.3)));
   q[Q_ua_inf] = m_rcp(1.0f + m_exp((Vs + 20.3f) * -FIB_RCPF(9.6)));
   {
     const float alpha = m_rcp(21.0f + 1.0f * m_exp((Vs - 195.000f) * -FIB_RCPF(28.0)));
     const float beta = m_exp((Vs - 168.0f) * 0.0625f);          // 1 / e^{-z} = e^{z}
-    q[Q_tau_ui] = m_rcp(alpha + beta) * FIB_RCPF(3.0);
+    q[Q_tau_ui] = RATES ? 3.0f * (alpha + beta) : m_rcp(alpha + beta) * FIB_RCPF(3.0);
   }
   q[Q_ui_inf] = m_rcp(1.0f + m_exp((Vs - 109.45f) * FIB_RCPF(27.48)));
   {
     const float w = V + 14.1f;
-    const float alpha = fabsf(w) < 1.0e-10f ? 0.0015f : m_div(0.0003f * w, 1.0f - m_exp(w * -0.2f));
     const float z = V - 3.3328f;
-    const float beta = fabsf(z) < 1.0e-10f
-                           ? 0.000378361f
-                           : m_div(7.3898e-05f * z, m_exp(z * FIB_RCPF(5.1237)) - 1.0f);
-    q[Q_tau_xr] = m_rcp(alpha + beta);
+    const bool sw = fabsf(w) < 1.0e-10f, sz = fabsf(z) < 1.0e-10f;
+    const float aN = sw ? 0.0015f : 0.0003f * w, aD = sw ? 1.0f : 1.0f - m_exp(w * -0.2f);
+    const float bN = sz ? 0.000378361f : 7.3898e-05f * z;
+    const float bD = sz ? 1.0f : m_exp(z * FIB_RCPF(5.1237)) - 1.0f;
+    if (RATES) q[Q_tau_xr] = fmaf(aN, bD, bN * aD) * m_rcp(aD * bD);
+    else q[Q_tau_xr] = m_rcp(m_div(aN, aD) + m_div(bN, bD));
     q[Q_xr_inf] = m_rcp(1.0f + m_exp(w * -FIB_RCPF(6.5)));
   }
   {
     const float w = V - 19.9f;
     const bool z = fabsf(w) < 1.0e-10f;
-    const float alpha = z ? 0.00068f : m_div(4.0e-05f * w, 1.0f - m_exp(w * -FIB_RCPF(17.0)));
-    const float beta = z ? 0.000315f : m_div(3.5e-05f * w, m_exp(w * FIB_RCPF(9.0)) - 1.0f);
-    q[Q_tau_xs] = 0.5f * m_rcp(alpha + beta);
+    const float aN = z ? 0.00068f : 4.0e-05f * w, aD = z ? 1.0f : 1.0f - m_exp(w * -FIB_RCPF(17.0));
+    const float bN = z ? 0.000315f : 3.5e-05f * w, bD = z ? 1.0f : m_exp(w * FIB_RCPF(9.0)) - 1.0f;
+    if (RATES) q[Q_tau_xs] = (2.0f * fmaf(aN, bD, bN * aD)) * m_rcp(aD * bD);
+    else q[Q_tau_xs] = 0.5f * m_rcp(m_div(aN, aD) + m_div(bN, bD));
     q[Q_xs_inf] = m_sqrt(m_rcp(1.0f + m_exp(w * -FIB_RCPF(12.7))));
   }
   q[Q_g_Kur] = 0.005f + 0.05f * m_rcp(1.0f + m_exp((V - 15.0f) * -FIB_RCPF(13.0)));
@@ -181,7 +220,7 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
     const float b_us = 1e-5f * (0.5f * (1.f + tanhf((V - (float)(-83.0 + 30)) * FIB_RCPF(23.0))));
     const float r = m_rcp(a_us + b_us);
     q[Q_us_inf] = a_us * r;
-    q[Q_tau_us] = r;
+    q[Q_tau_us] = RATES ? a_us + b_us : r;
   } else {
     q[Q_us_inf] = 0.f;
     q[Q_tau_us] = 1.f;
@@ -227,6 +266,13 @@ struct Courtemanche {
 
   static __device__ __forceinline__ void prologue(const StepArgs<Courtemanche>&) {}
 
+  // rush_larsen_b with t = tau (table flavours) or t = 1/tau (direct flavours)
+  static __device__ __forceinline__ float gate(float g, float g_inf, float t, float neg_dt,
+                                               const Params& p) {
+    const float e = m_expm1_neg(LUT ? m_div(neg_dt, t) : neg_dt * t);
+    return rush_larsen_eb(g, g_inf, e, p.clip_lo, p.clip_hi);
+  }
+
   static __device__ __forceinline__ void cell(const StepArgs<Courtemanche>& a, float /*raw*/,
                                               float V, float lap, float (&s)[NS], float& Vnew) {
     using namespace cc;
@@ -248,7 +294,7 @@ struct Courtemanche {
         q[Q_tau_us] = qq[Q_tau_us];
       }
     } else {
-      court_inter_dev<US>(V, q);
+      court_inter_dev<US, true>(V, q);                // Q_tau_* hold 1/tau
     }
     const float ndf = p.neg_dt_fast, nds = p.neg_dt_slow, dtf = p.dt_fast, dts = p.dt_slow;
     const float Na_i = s[S_Na_i], K_i = s[S_K_i], Ca_i = s[S_Ca_i], Ca_rel = s[S_Ca_rel],
@@ -257,25 +303,26 @@ struct Courtemanche {
                 ui = s[S_ui], xr = s[S_xr], xs = s[S_xs], d = s[S_d], f = s[S_f], f_Ca = s[S_f_Ca],
                 u = s[S_u], v = s[S_v], w = s[S_w];
 
-    // gates (court.py:175-189); _w_ is clocked with the step of '_d_' (court.py:177) = slow
-    s[S_d] = rush_larsen_b(d, q[Q_d_inf], q[Q_tau_d], nds, p.clip_lo, p.clip_hi);
-    s[S_f] = rush_larsen_b(f, q[Q_f_inf], q[Q_tau_f], nds, p.clip_lo, p.clip_hi);
-    s[S_w] = rush_larsen_b(w, q[Q_w_inf], q[Q_tau_w], nds, p.clip_lo, p.clip_hi);
-    s[S_m] = rush_larsen_b(m, q[Q_m_inf], q[Q_tau_m], ndf, p.clip_lo, p.clip_hi);
-    s[S_h] = rush_larsen_b(h, q[Q_h_inf], q[Q_tau_h], ndf, p.clip_lo, p.clip_hi);
-    s[S_j] = rush_larsen_b(j, q[Q_j_inf], q[Q_tau_j], nds, p.clip_lo, p.clip_hi);
-    s[S_oa] = rush_larsen_b(oa, q[Q_oa_inf], q[Q_tau_oa], nds, p.clip_lo, p.clip_hi);
-    s[S_oi] = rush_larsen_b(oi, q[Q_oi_inf], q[Q_tau_oi], nds, p.clip_lo, p.clip_hi);
-    s[S_ua] = rush_larsen_b(ua, q[Q_ua_inf], q[Q_tau_ua], nds, p.clip_lo, p.clip_hi);
-    s[S_ui] = rush_larsen_b(ui, q[Q_ui_inf], q[Q_tau_ui], nds, p.clip_lo, p.clip_hi);
-    s[S_xr] = rush_larsen_b(xr, q[Q_xr_inf], q[Q_tau_xr], nds, p.clip_lo, p.clip_hi);
-    s[S_xs] = rush_larsen_b(xs, q[Q_xs_inf], q[Q_tau_xs], nds, p.clip_lo, p.clip_hi);
+    // gates (court.py:175-189); _w_ is clocked with the step of '_d_' (court.py:177) = slow.
+    // `gate` takes tau from the table and 1/tau from the direct evaluation (court_inter_dev).
+    s[S_d] = gate(d, q[Q_d_inf], q[Q_tau_d], nds, p);
+    s[S_f] = gate(f, q[Q_f_inf], q[Q_tau_f], nds, p);
+    s[S_w] = gate(w, q[Q_w_inf], q[Q_tau_w], nds, p);
+    s[S_m] = gate(m, q[Q_m_inf], q[Q_tau_m], ndf, p);
+    s[S_h] = gate(h, q[Q_h_inf], q[Q_tau_h], ndf, p);
+    s[S_j] = gate(j, q[Q_j_inf], q[Q_tau_j], nds, p);
+    s[S_oa] = gate(oa, q[Q_oa_inf], q[Q_tau_oa], nds, p);
+    s[S_oi] = gate(oi, q[Q_oi_inf], q[Q_tau_oi], nds, p);
+    s[S_ua] = gate(ua, q[Q_ua_inf], q[Q_tau_ua], nds, p);
+    s[S_ui] = gate(ui, q[Q_ui_inf], q[Q_tau_ui], nds, p);
+    s[S_xr] = gate(xr, q[Q_xr_inf], q[Q_tau_xr], nds, p);
+    s[S_xs] = gate(xs, q[Q_xs_inf], q[Q_tau_xs], nds, p);
     const float f_Ca_inf = m_rcp(1.0f + Ca_i * FIB_RCPF(0.00035));
     s[S_f_Ca] = rush_larsen_eb(f_Ca, f_Ca_inf, p.e_fCa, p.clip_lo, p.clip_hi);
     float us = 1.f;
     if (US) {
       us = s[S_us];
-      s[S_us] = rush_larsen_b(us, q[Q_us_inf], q[Q_tau_us], nds, p.clip_lo, p.clip_hi);   // court_ultra.py:198-199
+      s[S_us] = gate(us, q[Q_us_inf], q[Q_tau_us], nds, p);   // court_ultra.py:198-199
     }
 
     // currents (court.py:191-221)

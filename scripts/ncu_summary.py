@@ -31,7 +31,7 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 CELLS = 4096 * 4096
 traffic = {}
 lines = []
-for rep, key, balg in (('prof_4v', 'fenton4v_step', 32), ('prof_br', 'br_cheby_step', 64),
+for rep, key, balg in (('prof_4v', 'fenton4v_step', 32), ('prof_br', 'br_cheby_step', 64), ('prof_br_exact', 'br_exact_step', 64),
                        ('prof_court', 'court_ultra_step', 168)):
     path = os.path.join(G, rep + '.ncu-rep')
     if not os.path.exists(path):
