@@ -526,3 +526,57 @@ def test_cuda_is_as_close_to_exact_arithmetic_as_the_reference(cuda, name):
         e_cuda = onp.rel_err(out[v], truth, fl)
         assert e_cuda <= max(1e-5, 2.5 * e_ref), '%s %s: cuda %.2e vs reference %.2e from exact' % (
             name, v, e_cuda, e_ref)
+
+
+@pytest.mark.parametrize('flags', [dict(cheby=False, skip=False), dict(cheby=False, skip=True),
+                                   dict(cheby=True, skip=False)])
+def test_beeler_reuter_removable_singularities(cuda, flags):
+    """br.py:150-151 and the alpha_m of br.py:52 are 0/0 at V == -23.0 and V == -47.0 exactly; the
+    reference's GPU clip turns the NaN into the upper bound (fib_common.cuh: clip_tf).  The kernel
+    evaluates both terms through an expm1 polynomial within ~3 mV of the singular points and reuses
+    exponentials across gates, so this test plants cells exactly on, next to and around the switch
+    points (|0.04 (V+23)|, |0.1 (V+47)| = 0.125), plus a sweep over the whole clipped voltage range,
+    in a diffusion-free grid (every cell an independent ODE) and requires the first iteration (5
+    time steps) to agree with the oracle.  Cells within 0.3 mV of a singular point (but not on it)
+    are skipped: there the reference's own fp32 cancellation is worse than 1e-5."""
+    H, W = 34, 131
+    cfg = {'width': W, 'height': H, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 0.0, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False}
+    cfg.update(flags)
+    deltas = [0.0, 0.5, -0.5, 1.0, -1.0, 1.2, -1.3, 3.0, -3.0, 3.12, -3.12, 3.13, -3.13, 3.2, -3.2, 6.0, -6.0]
+    special = np.float32([s + d for s in (-23.0, -47.0) for d in deltas])
+    rng = np.random.default_rng(5)
+    V = rng.uniform(-85.0, 25.0, size=(H, W)).astype(np.float32)
+    V.flat[:4 * special.size] = np.tile(special, 4)
+    rng.shuffle(V.reshape(-1))
+    near = np.zeros_like(V, bool)
+    for s in (-23.0, -47.0):
+        near |= (np.abs(V - np.float32(s)) < 0.3) & (V != np.float32(s))
+    assert (V == np.float32(-23.0)).sum() >= 4 and (V == np.float32(-47.0)).sum() >= 4
+    state = {'V': V, 'C': rng.uniform(5e-5, 5e-3, (H, W)).astype(np.float32)}
+    for g in ('M', 'H', 'J', 'D', 'F', 'XI'):
+        state[g] = rng.uniform(1e-3, 0.998, (H, W)).astype(np.float32)
+    ref, gpu = onp.OracleModel('br', cfg), cuda.CudaModel('br', cfg)
+    ref.define(s1=False)
+    gpu.define(s1=False)
+    for k, a in state.items():
+        ref.state[k] = a.copy()
+        gpu.m._State[k].assign(a)
+    with np.errstate(all='ignore'):
+        ref.iterate()
+    gpu.iterate()
+    inner = np.zeros((H, W), bool)
+    inner[1:-1, 1:-1] = True                      # the border ring is overwritten by enforce_boundary
+    keep = inner & ~near
+    # exact gates: measured worst 2.3e-5 (C of the cells that took the NaN path, 5 steps later);
+    # polynomial gates: the fixtures' own rounding noise (the S-basis sum, model_br.cuh)
+    tol = max(1e-5, 3 * model_noise('br')) if flags['cheby'] else 5e-5
+    for v in ref.state:
+        got, want = gpu.state[v], ref.state[v]
+        assert np.isfinite(got[inner]).all() and np.isfinite(want[inner]).all(), v
+        e = onp.rel_err(got[keep], want[keep], onp.var_floor('br', v))
+        assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (flags, v, e, tol)
+    # the cells planted ON the singular points took the reference's NaN -> upper clip bound path
+    on23 = inner & (V == np.float32(-23.0))
+    assert on23.any() and (gpu.state['V'][on23] > 15.0).all() and (ref.state['V'][on23] > 15.0).all()
+    gpu.close()
