@@ -77,18 +77,43 @@ template <bool WANT_US, bool RATES = false>
 __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols]) {
   using namespace cc;
   const float eps = V * 1e-20f;
+
+  // The six removable singularities (tau_d at -10.0001 mV, tau_w at 7.9, alpha/beta of xr at -14.1
+  // and 3.3328, of xs at 19.9) are x/(e^y - 1) shapes that the reference guards only at x == 0
+  // exactly (court.py:316-327,398-413).  One ulp away y is ~5e-8 and e^y - 1 from the SFU
+  // exponential can be exactly 0 with the wrong sign, i.e. a rate of -inf and a gate thrown onto
+  // its clip bound -- correctly rounded expf never does that at these magnitudes.  So e^y - 1 comes
+  // from the expm1 polynomial when |y| < 0.03 (beyond, e^y - 1 is within 4e-6).  The fix-up sits
+  // behind a warp vote because it is rare; each lane's result depends on its own y only.
+  const float wd = V + 10.0001f, ww = V - 7.9f, wr = V + 14.1f, zr = V - 3.3328f, ws = V - 19.9f;
+  const float y[6] = {wd * -FIB_RCPF(6.24), -ww * 0.2f, wr * -0.2f, zr * FIB_RCPF(5.1237),
+                      ws * -FIB_RCPF(17.0), ws * FIB_RCPF(9.0)};
+  float ey[6], em1[6];
+  float ymin = 1.0f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    ey[k] = m_exp(y[k]);
+    em1[k] = ey[k] - 1.0f;
+    ymin = fminf(ymin, fabsf(y[k]));
+  }
+#if !FIB_ACCURATE_MATH
+  if (__any_sync(__activemask(), ymin < 0.03f)) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) em1[k] = fabsf(y[k]) < 0.03f ? m_expm1(y[k]) : em1[k];
+  }
+#endif
+
   q[Q_d_inf] = m_rcp(1.0f + m_exp((V + 10.0f) * -0.125f));
   {
-    const float w = V + 10.0001f;
-    const float e = m_exp(w * -FIB_RCPF(6.24));
+    const float w = wd, e = ey[0], one_m_e = -em1[0];
     if (RATES)
       q[Q_tau_d] = fabsf(w) < 1.0e-10f
                        ? (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24))) / 4.579f
-                       : m_div(0.0350000f * w * (1.0f + e), 1.0f - e);
+                       : m_div(0.0350000f * w * (1.0f + e), one_m_e);
     else
       q[Q_tau_d] = fabsf(w) < 1.0e-10f
                        ? 4.579f / (1.0f + expf((V + 10.0f) * -FIB_RCPF(6.24)))
-                       : m_div(1.0f - e, 0.0350000f * w * (1.0f + e));
+                       : m_div(one_m_e, 0.0350000f * w * (1.0f + e));
   }
   {
     const float e = m_exp(-(V + 28.0f) * FIB_RCPF(6.9));
@@ -100,14 +125,13 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
     q[Q_tau_f] = RATES ? x * FIB_RCPF(9.0) : 9.0f * m_rcp(x);
   }
   {
-    const float w = V - 7.9f;
-    const float e = m_exp(-w * 0.2f);
+    const float w = ww, e = ey[1], one_m_e = -em1[1];
     if (RATES)
       q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)(1.3 / (6.0 * 0.2))
-                                       : m_div((1.0f + 0.3f * e) * 1.0f * w, 6.0f * (1.0f - e));
+                                       : m_div((1.0f + 0.3f * e) * 1.0f * w, 6.0f * one_m_e);
     else
       q[Q_tau_w] = fabsf(w) < 1.0e-10f ? (float)((6.0 * 0.2) / 1.3)
-                                       : m_div(6.0f * (1.0f - e), (1.0f + 0.3f * e) * 1.0f * w);
+                                       : m_div(6.0f * one_m_e, (1.0f + 0.3f * e) * 1.0f * w);
   }
   q[Q_w_inf] = 1.0f - m_rcp(1.0f + m_exp(-(V - 40.0f) * FIB_RCPF(17.0)));
   {
@@ -182,12 +206,11 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
   }
   q[Q_ui_inf] = m_rcp(1.0f + m_exp((Vs - 109.45f) * FIB_RCPF(27.48)));
   {
-    const float w = V + 14.1f;
-    const float z = V - 3.3328f;
+    const float w = wr, z = zr;
     const bool sw = fabsf(w) < 1.0e-10f, sz = fabsf(z) < 1.0e-10f;
-    const float aN = sw ? 0.0015f : 0.0003f * w, aD = sw ? 1.0f : 1.0f - m_exp(w * -0.2f);
+    const float aN = sw ? 0.0015f : 0.0003f * w, aD = sw ? 1.0f : -em1[2];    // 1 - e^{-0.2 w}
     const float bN = sz ? 0.000378361f : 7.3898e-05f * z;
-    const float bD = sz ? 1.0f : m_exp(z * FIB_RCPF(5.1237)) - 1.0f;
+    const float bD = sz ? 1.0f : em1[3];                                       // e^{z/5.1237} - 1
     if (RATES) q[Q_tau_xr] = fmaf(aN, bD, bN * aD) * m_rcp(aD * bD);
     else q[Q_tau_xr] = m_rcp(m_div(aN, aD) + m_div(bN, bD));
     q[Q_xr_inf] = m_rcp(1.0f + m_exp(w * -FIB_RCPF(6.5)));
@@ -195,8 +218,8 @@ __device__ __forceinline__ void court_inter_dev(float V, float (&q)[kInterCols])
   {
     const float w = V - 19.9f;
     const bool z = fabsf(w) < 1.0e-10f;
-    const float aN = z ? 0.00068f : 4.0e-05f * w, aD = z ? 1.0f : 1.0f - m_exp(w * -FIB_RCPF(17.0));
-    const float bN = z ? 0.000315f : 3.5e-05f * w, bD = z ? 1.0f : m_exp(w * FIB_RCPF(9.0)) - 1.0f;
+    const float aN = z ? 0.00068f : 4.0e-05f * w, aD = z ? 1.0f : -em1[4];   // 1 - e^{-w/17}
+    const float bN = z ? 0.000315f : 3.5e-05f * w, bD = z ? 1.0f : em1[5];    // e^{w/9} - 1
     if (RATES) q[Q_tau_xs] = (2.0f * fmaf(aN, bD, bN * aD)) * m_rcp(aD * bD);
     else q[Q_tau_xs] = 0.5f * m_rcp(m_div(aN, aD) + m_div(bN, bD));
     q[Q_xs_inf] = m_sqrt(m_rcp(1.0f + m_exp(w * -FIB_RCPF(12.7))));

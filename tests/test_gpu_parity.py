@@ -580,3 +580,65 @@ def test_beeler_reuter_removable_singularities(cuda, flags):
     on23 = inner & (V == np.float32(-23.0))
     assert on23.any() and (gpu.state['V'][on23] > 15.0).all() and (ref.state['V'][on23] > 15.0).all()
     gpu.close()
+
+
+def test_courtemanche_removable_singularities(cuda):
+    """court.py:316-327,398-413: tau_d, tau_w and the alpha/beta of xr and xs are x/(e^y - 1) shapes
+    guarded only at x == 0 exactly.  One ulp next to a singular voltage the reference's own fp32
+    result is noise (its e^y - 1 has no correct digit; for V one ulp above 3.3328 mV it is exactly
+    0, i.e. tau_xr = 0 and xr jumps to its steady state), so those cells are checked against the
+    SAME formulas evaluated in float64, where the kernel (expm1 polynomial behind a warp vote,
+    model_court.cuh) must be accurate; all other cells are checked against the fp32 oracle."""
+    H, W, dt = 20, 66, 0.1
+    cfg = {'width': W, 'height': H, 'dt': dt, 'dt_per_plot': 10, 'diff': 0.0, 'duration': 1,
+           'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'ultra_slow': False}
+    sing = np.float32([-10.0001, 7.9, -14.1, 3.3328, 19.9])
+    vals = []
+    for s in sing:
+        for k in (0, 1, -1, 2, -2, 3, -3, 10, -10, 1000, -1000, 30000, -30000):
+            v = np.float32(s)
+            for _ in range(abs(k)):
+                v = np.nextafter(v, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+            vals.append(v)
+    vals = np.float32(vals)
+    rng = np.random.default_rng(7)
+    V = rng.uniform(-90.0, 40.0, size=(H, W)).astype(np.float32)
+    V.flat[:4 * vals.size] = np.tile(vals, 4)
+    rng.shuffle(V.reshape(-1))
+    gates = ('_m_', '_h_', '_j_', '_oa_', '_oi_', '_ua_', '_ui_', '_xr_', '_xs_', '_d_', '_f_', '_f_Ca_',
+             '_u_', '_v_', '_w_')
+    ref, gpu = onp.OracleModel('court_ultra', cfg), cuda.CudaModel('court_ultra', cfg)
+    ref.define(s1=False)
+    gpu.define(s1=False)
+    init = {k: a.copy() for k, a in ref.state.items()}
+    init['V'] = V
+    for g in gates:
+        init[g] = rng.uniform(1e-3, 0.998, (H, W)).astype(np.float32)
+    for k, a in init.items():
+        ref.state[k] = a.copy()
+        gpu.m._State[k].assign(a)
+    with np.errstate(all='ignore'):
+        ref.iterate()
+    gpu.iterate()
+    inner = np.zeros((H, W), bool)
+    inner[1:-1, 1:-1] = True
+    near = np.zeros((H, W), bool)
+    for s in sing:
+        near |= np.abs(V - s) < 0.5
+    assert (near & inner).sum() >= 100
+    for v in ref.state:
+        got, want = gpu.state[v], ref.state[v]
+        assert np.isfinite(got).all(), v
+        keep = inner & ~near
+        e = onp.rel_err(got[keep], want[keep], onp.var_floor('court_ultra', v))
+        assert e <= 5e-5, (v, e)
+    # every cell, near-singular ones included, against float64: g + (g - g_inf) expm1(-dt / tau)
+    with np.errstate(all='ignore'):
+        q = onp.court_inter(V.astype(np.float64))
+    for g, inf, tau in (('_d_', 'd_infinity', 'tau_d'), ('_w_', 'w_infinity', 'tau_w'),
+                        ('_xr_', 'xr_infinity', 'tau_xr'), ('_xs_', 'xs_infinity', 'tau_xs')):
+        g0 = init[g].astype(np.float64)
+        exact = np.clip(g0 + (g0 - q[inf]) * np.expm1(-dt / q[tau]), 1e-5, 0.99999)
+        e = onp.rel_err(gpu.state[g][inner], exact[inner], onp.var_floor('court_ultra', g))
+        assert e <= 2e-5, (g, e)
+    gpu.close()
