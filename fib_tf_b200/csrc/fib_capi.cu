@@ -15,6 +15,7 @@
 #include "model_br.cuh"
 #include "model_court.cuh"
 #include "model_fenton.cuh"
+#include "fib_fused.cuh"
 
 using namespace fib;
 
@@ -114,6 +115,8 @@ struct fib_ctx {
               ev_group = nullptr;
   float* x[2] = {nullptr, nullptr};   // diffusing variable, ping-pong, halo layout
   int cur = 0;
+  int fuse = 1;                       // time steps per launch (cfg.steps_per_launch): 1 or 2
+  float* fx[2][4] = {{nullptr}};      // fuse == 2 (fib_fused.cuh): ALL planes ping-ponged, kFuseHalo rows
   float* s[S_COUNT] = {nullptr};      // other planes
   float* phase = nullptr;             // halo layout
   unsigned char* pmask = nullptr;     // [rows][pmask_pitch] non-trivial-phase flags per 32 columns
@@ -131,6 +134,7 @@ struct fib_ctx {
   int nranks = 1, rank = 0;
   size_t plane_floats() const { return (size_t)g.rows * g.pitch; }
   size_t halo_floats() const { return (size_t)(g.rows + 2) * g.pitch; }
+  size_t fused_floats() const { return (size_t)(g.rows + 2 * kFuseHalo) * g.pitch; }
   bool top_is_border() const { return g.row0 == 0; }
   bool bottom_is_border() const { return g.row0 + g.rows == g.H; }
 };
@@ -259,15 +263,19 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
     return fail(FIB_E_ARG, "grid %dx%d too small: the two-stage boundary needs >= 3x3", cfg->height,
                 cfg->width);
   if (!(cfg->dt > 0.0)) return fail(FIB_E_ARG, "dt must be > 0");
-  if (cfg->steps_per_launch > 1)
-    return fail(FIB_E_ARG, "steps_per_launch=%d: temporal blocking is not available in this build",
-                cfg->steps_per_launch);
+  if (cfg->steps_per_launch < 0 || cfg->steps_per_launch > 2)
+    return fail(FIB_E_ARG, "steps_per_launch=%d: 0/1 (one step per launch) or 2", cfg->steps_per_launch);
+  if (cfg->steps_per_launch == 2 && (cfg->model != FIB_FENTON4V || cfg->width % 4 != 0))
+    return fail(FIB_E_ARG, "steps_per_launch=2 needs the Fenton 4v model and a width that is a multiple "
+                "of 4 (got model %d, width %d)", cfg->model, cfg->width);
   int rows = cfg->rows == 0 ? cfg->height : cfg->rows;
   int row0 = cfg->rows == 0 ? 0 : cfg->row0;
   if (row0 < 0 || rows < 1 || row0 + rows > cfg->height)
     return fail(FIB_E_ARG, "shard rows [%d,%d) outside the grid of height %d", row0, row0 + rows,
                 cfg->height);
-  if ((long long)(rows + 2) * ((cfg->width + 31) / 32 * 32) >= (1LL << 31))
+  if (cfg->steps_per_launch == 2 && rows != cfg->height && rows < kFuseHalo)
+    return fail(FIB_E_ARG, "steps_per_launch=2: a shard must own at least %d rows (got %d)", kFuseHalo, rows);
+  if ((long long)(rows + 2 * kFuseHalo) * ((cfg->width + 31) / 32 * 32) >= (1LL << 31))
     return fail(FIB_E_ARG, "shard of %d rows x %d columns exceeds 2^31 cells per plane: the kernels "
                 "index planes with 32-bit element offsets; shard the grid over more GPUs", rows,
                 cfg->width);
@@ -306,13 +314,22 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   CU(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_group, cudaEventDisableTiming));
-  for (int b = 0; b < 2; ++b) {
-    CU(cudaMalloc(&c->x[b], c->halo_floats() * sizeof(float)));
-    CU(cudaMemsetAsync(c->x[b], 0, c->halo_floats() * sizeof(float), c->stream));
-  }
-  for (int k = 0; k + 1 < c->nvars; ++k) {
-    CU(cudaMalloc(&c->s[k], c->plane_floats() * sizeof(float)));
-    CU(cudaMemsetAsync(c->s[k], 0, c->plane_floats() * sizeof(float), c->stream));
+  c->fuse = cfg->steps_per_launch == 2 ? 2 : 1;
+  if (c->fuse == 2) {
+    for (int b = 0; b < 2; ++b)
+      for (int v = 0; v < 4; ++v) {
+        CU(cudaMalloc(&c->fx[b][v], c->fused_floats() * sizeof(float)));
+        CU(cudaMemsetAsync(c->fx[b][v], 0, c->fused_floats() * sizeof(float), c->stream));
+      }
+  } else {
+    for (int b = 0; b < 2; ++b) {
+      CU(cudaMalloc(&c->x[b], c->halo_floats() * sizeof(float)));
+      CU(cudaMemsetAsync(c->x[b], 0, c->halo_floats() * sizeof(float), c->stream));
+    }
+    for (int k = 0; k + 1 < c->nvars; ++k) {
+      CU(cudaMalloc(&c->s[k], c->plane_floats() * sizeof(float)));
+      CU(cudaMemsetAsync(c->s[k], 0, c->plane_floats() * sizeof(float), c->stream));
+    }
   }
   CU(cudaMalloc(&c->red, 2 * sizeof(double)));
   if (cfg->model >= FIB_COURT) {
@@ -339,6 +356,8 @@ extern "C" int fib_destroy(fib_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
   for (int b = 0; b < 2; ++b) cudaFree(c->x[b]);
+  for (int b = 0; b < 2; ++b)
+    for (int v = 0; v < 4; ++v) cudaFree(c->fx[b][v]);
   for (int k = 0; k < S_COUNT; ++k) cudaFree(c->s[k]);
   cudaFree(c->phase);
   cudaFree(c->pmask);
@@ -369,9 +388,21 @@ extern "C" int fib_var_index(const fib_ctx* c, const char* name) {
 }
 extern "C" int fib_dt_per_step(const fib_ctx* c) { return c ? c->dt_per_step : fail(FIB_E_ARG, "ctx is NULL"); }
 
-// plane base pointer of the first OWNED row + whether the plane is in halo layout
+// A plane of the CURRENT state: start of its allocation and the number of halo rows above the
+// first owned row (1 for the diffusing variable, 0 for the in-place planes, kFuseHalo for every
+// plane of the two-steps-per-launch layout).
+struct PlaneRef { float* base; int halo; };
+static PlaneRef plane_of(fib_ctx* c, int var) {
+  if (c->fuse == 2) return {c->fx[c->cur][var], kFuseHalo};
+  return var == 0 ? PlaneRef{c->x[c->cur], 1} : PlaneRef{c->s[var - 1], 0};
+}
 static float* owned_rows(fib_ctx* c, int var) {
-  return var == 0 ? c->x[c->cur] + c->g.pitch : c->s[var - 1];
+  const PlaneRef p = plane_of(c, var);
+  return p.base + (size_t)p.halo * c->g.pitch;
+}
+// a host write into `var` invalidates the neighbours' copies of the rows they hold as halo
+static void mark_written(fib_ctx* c, int var) {
+  if (var == 0 || c->fuse == 2) c->halo_dirty = true;
 }
 
 extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
@@ -383,7 +414,7 @@ extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
   CU(cudaMemcpy2DAsync(owned_rows(c, var), c->g.pitch * sizeof(float), host, c->g.W * sizeof(float),
                        c->g.W * sizeof(float), c->g.rows, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (var == 0) c->halo_dirty = true;
+  mark_written(c, var);
   return 0;
 }
 
@@ -450,12 +481,14 @@ extern "C" int fib_set_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1,
   CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)(c1 - c0) * sizeof(float),
                        (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (var == 0) c->halo_dirty = true;
+  mark_written(c, var);
   return 0;
 }
 
 extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (c->fuse == 2 && rows_host)
+    return fail(FIB_E_STATE, "a phase field is not available with steps_per_launch=2");
   DevGuard dg(c->cfg.device);
   CU(cudaStreamSynchronize(c->stream));
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);   // graphs bake the phase pointer in
@@ -623,6 +656,17 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
   cudaError_t e = cudaSuccess;
   switch (c->cfg.model) {
     case FIB_FENTON4V: {
+      if (c->fuse == 2) {                       // time steps `sub` and `sub + 1` in one launch
+        Fused2Args f;
+        for (int v = 0; v < 4; ++v) { f.in[v] = c->fx[c->cur][v]; f.out[v] = c->fx[c->cur ^ 1][v]; }
+        f.lr0 = lr0;
+        f.nrows = nrows;
+        f.R = 0;
+        f.p.dt = (float)dt;
+        f.p.ddt = (float)(c->cfg.diff * dt);
+        e = launch_fused2(c->g, f, c->stream, c->sms);
+        break;
+      }
       StepArgs<Fenton4v> a;
       fill_common<Fenton4v>(c, a, lr0, nrows);
       a.p.dt = (float)dt;
@@ -679,7 +723,28 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
 static bool op_writes_x(const fib_ctx* c, int op) { return !(c->cfg.model == FIB_COURT && op == FIB_OP_SLOW); }
 
 // ---- NCCL halo exchange of buffer `buf` (rows just written), on `st` ------------------------
-static int nccl_exchange(fib_ctx* c, float* buf, cudaStream_t st) {
+// fuse == 2: kFuseHalo rows of every plane of buffer set `b` (rows are pitch-contiguous)
+static int nccl_exchange_fused(fib_ctx* c, int b, cudaStream_t st) {
+  const size_t P = c->g.pitch, n = (size_t)kFuseHalo * P;
+  NC(g_nccl.GroupStart());
+  for (int v = 0; v < 4; ++v) {
+    float* buf = c->fx[b][v];
+    if (c->rank > 0) {
+      NC(g_nccl.Send(buf + n, n, kNcclFloat, c->rank - 1, c->comm, st));
+      NC(g_nccl.Recv(buf, n, kNcclFloat, c->rank - 1, c->comm, st));
+    }
+    if (c->rank + 1 < c->nranks) {
+      NC(g_nccl.Send(buf + (size_t)c->g.rows * P, n, kNcclFloat, c->rank + 1, c->comm, st));
+      NC(g_nccl.Recv(buf + (size_t)c->g.rows * P + n, n, kNcclFloat, c->rank + 1, c->comm, st));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+static int nccl_exchange(fib_ctx* c, int b, cudaStream_t st) {
+  if (c->fuse == 2) return nccl_exchange_fused(c, b, st);
+  float* buf = c->x[b];
   const size_t W = c->g.W, P = c->g.pitch;
   NC(g_nccl.GroupStart());
   if (c->rank > 0) {
@@ -696,7 +761,7 @@ static int nccl_exchange(fib_ctx* c, float* buf, cudaStream_t st) {
 
 static int run_iteration_plain(fib_ctx* c, int op) {
   const int ns = substeps_of(c, op);
-  for (int s = 0; s < ns; ++s) {
+  for (int s = 0; s < ns; s += c->fuse) {
     int r = launch_substep(c, op, s, 0, c->g.rows);
     if (r) return r;
     if (op_writes_x(c, op)) c->cur ^= 1;
@@ -708,7 +773,8 @@ static int run_iteration_plain(fib_ctx* c, int op) {
 static int run_iteration_nccl(fib_ctx* c, int op) {
   const int ns = substeps_of(c, op);
   const int rows = c->g.rows;
-  for (int s = 0; s < ns; ++s) {
+  const int nb = c->fuse;      // rows the neighbours need from each edge = time steps per launch
+  for (int s = 0; s < ns; s += c->fuse) {
     if (!op_writes_x(c, op)) {
       int r = launch_substep(c, op, s, 0, rows);
       if (r) return r;
@@ -719,18 +785,18 @@ static int run_iteration_nccl(fib_ctx* c, int op) {
       c->comm_pending = false;
     }
     int r;
-    if (rows >= 3) {
-      if ((r = launch_substep(c, op, s, 0, 1))) return r;
-      if ((r = launch_substep(c, op, s, rows - 1, 1))) return r;
+    if (rows >= 3 * nb) {
+      if ((r = launch_substep(c, op, s, 0, nb))) return r;
+      if ((r = launch_substep(c, op, s, rows - nb, nb))) return r;
       CU(cudaEventRecord(c->ev_bnd, c->stream));
       CU(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-      if ((r = nccl_exchange(c, c->x[c->cur ^ 1], c->comm_stream))) return r;
+      if ((r = nccl_exchange(c, c->cur ^ 1, c->comm_stream))) return r;
       CU(cudaEventRecord(c->ev_comm, c->comm_stream));
       c->comm_pending = true;
-      if ((r = launch_substep(c, op, s, 1, rows - 2))) return r;
+      if ((r = launch_substep(c, op, s, nb, rows - 2 * nb))) return r;
     } else {
       if ((r = launch_substep(c, op, s, 0, rows))) return r;
-      if ((r = nccl_exchange(c, c->x[c->cur ^ 1], c->stream))) return r;
+      if ((r = nccl_exchange(c, c->cur ^ 1, c->stream))) return r;
     }
     c->cur ^= 1;
   }
@@ -739,7 +805,7 @@ static int run_iteration_nccl(fib_ctx* c, int op) {
 
 static int refresh_halos_nccl(fib_ctx* c) {
   if (!c->halo_dirty) return 0;
-  int r = nccl_exchange(c, c->x[c->cur], c->stream);
+  int r = nccl_exchange(c, c->cur, c->stream);
   if (r) return r;
   c->halo_dirty = false;
   return 0;
@@ -790,9 +856,9 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
       c->graphs.push_back({op, cur0, exec});
     }
     CU(cudaGraphLaunch(exec, c->stream));
-    const int ns = substeps_of(c, op);
-    c->launches += ns;
-    if (op_writes_x(c, op) && (ns & 1)) c->cur ^= 1;
+    const int nl = substeps_of(c, op) / c->fuse;      // launches per iteration
+    c->launches += nl;
+    if (op_writes_x(c, op) && (nl & 1)) c->cur ^= 1;
   }
   return 0;
 }
@@ -800,23 +866,33 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
 // ---- in-process shard group: lock-step, device-to-device halo copies ------------------------
 static int group_copy_halos(fib_ctx** cs, int n, bool written_buffer) {
   // copies the boundary rows of buffer (cur^1 if written_buffer else cur) into the neighbours'
-  // halo rows, each on the SOURCE stream, then records ev_group on every stream.
+  // halo rows, each on the SOURCE stream, then records ev_group on every stream.  One row of the
+  // diffusing variable, or kFuseHalo rows of every plane in the two-steps-per-launch layout.
   for (int i = 0; i < n; ++i) {
     fib_ctx* c = cs[i];
     DevGuard dg(c->cfg.device);
     const int b = written_buffer ? (c->cur ^ 1) : c->cur;
-    const size_t P = c->g.pitch, Wb = c->g.W * sizeof(float);
-    if (i > 0) {
-      fib_ctx* up = cs[i - 1];
-      const int ub = written_buffer ? (up->cur ^ 1) : up->cur;
-      CU(cudaMemcpyPeerAsync(up->x[ub] + (size_t)(up->g.rows + 1) * up->g.pitch, up->cfg.device,
-                             c->x[b] + P, c->cfg.device, Wb, c->stream));
-    }
-    if (i + 1 < n) {
-      fib_ctx* dn = cs[i + 1];
-      const int db = written_buffer ? (dn->cur ^ 1) : dn->cur;
-      CU(cudaMemcpyPeerAsync(dn->x[db], dn->cfg.device, c->x[b] + (size_t)c->g.rows * P,
-                             c->cfg.device, Wb, c->stream));
+    const bool fused = c->fuse == 2;
+    const int nplanes = fused ? 4 : 1, hr = fused ? kFuseHalo : 1;
+    const size_t P = c->g.pitch;
+    // one row: W floats; several rows: pitch-contiguous block
+    const size_t bytes = (hr == 1 ? (size_t)c->g.W : (size_t)hr * P) * sizeof(float);
+    for (int v = 0; v < nplanes; ++v) {
+      float* mine = fused ? c->fx[b][v] : c->x[b];
+      if (i > 0) {
+        fib_ctx* up = cs[i - 1];
+        const int ub = written_buffer ? (up->cur ^ 1) : up->cur;
+        float* theirs = fused ? up->fx[ub][v] : up->x[ub];
+        CU(cudaMemcpyPeerAsync(theirs + (size_t)(up->g.rows + hr) * up->g.pitch, up->cfg.device,
+                               mine + (size_t)hr * P, c->cfg.device, bytes, c->stream));
+      }
+      if (i + 1 < n) {
+        fib_ctx* dn = cs[i + 1];
+        const int db = written_buffer ? (dn->cur ^ 1) : dn->cur;
+        float* theirs = fused ? dn->fx[db][v] : dn->x[db];
+        CU(cudaMemcpyPeerAsync(theirs, dn->cfg.device, mine + (size_t)c->g.rows * P, c->cfg.device,
+                               bytes, c->stream));
+      }
     }
     CU(cudaEventRecord(c->ev_group, c->stream));
   }
@@ -839,7 +915,8 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
   for (int i = 0; i < n; ++i) {
     if (!cs[i]) return fail(FIB_E_ARG, "shard %d is NULL", i);
     if (cs[i]->g.row0 != row || cs[i]->g.H != cs[0]->g.H || cs[i]->g.W != cs[0]->g.W ||
-        cs[i]->cfg.model != cs[0]->cfg.model || cs[i]->cfg.flags != cs[0]->cfg.flags)
+        cs[i]->cfg.model != cs[0]->cfg.model || cs[i]->cfg.flags != cs[0]->cfg.flags ||
+        cs[i]->fuse != cs[0]->fuse)
       return fail(FIB_E_ARG, "shard %d is not the row-adjacent continuation of shard %d", i, i - 1);
     row += cs[i]->g.rows;
   }
@@ -869,7 +946,7 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
     for (int i = 0; i < n; ++i) cs[i]->halo_dirty = false;
   }
   for (int it = 0; it < n_iter; ++it)
-    for (int s = 0; s < ns; ++s) {
+    for (int s = 0; s < ns; s += cs[0]->fuse) {
       for (int i = 0; i < n; ++i) {
         DevGuard dg(cs[i]->cfg.device);
         if ((r = launch_substep(cs[i], op, s, 0, cs[i]->g.rows))) return r;
@@ -896,11 +973,11 @@ extern "C" int fib_stimulate(fib_ctx* c, int var, int r0, int r1, int c0, int c1
     c->comm_pending = false;
   }
   dim3 block(128), grid((c->g.W + 127) / 128, min(c->g.rows, 65535));
-  float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
-  stim_kernel<<<grid, block, 0, c->stream>>>(base, c->g, var == 0 ? 1 : 0, r0, r1, c0, c1, value, floor_v);
+  const PlaneRef pl = plane_of(c, var);
+  stim_kernel<<<grid, block, 0, c->stream>>>(pl.base, c->g, pl.halo, r0, r1, c0, c1, value, floor_v);
   CU(cudaGetLastError());
   c->launches++;
-  if (var == 0) c->halo_dirty = true;
+  mark_written(c, var);
   return 0;
 }
 
@@ -926,8 +1003,8 @@ extern "C" int fib_weighted_sum(fib_ctx* c, int var, double* sum_wx, double* sum
 
 static int reduce_weighted(fib_ctx* c, int var, const float* w, double* sum_wx, double* sum_w) {
   CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
-  const float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
-  wsum_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(base, w, c->g, var == 0 ? 1 : 0, c->red);
+  const PlaneRef pl = plane_of(c, var);
+  wsum_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(pl.base, w, c->g, pl.halo, c->red);
   CU(cudaGetLastError());
   c->launches++;
   double h[2];
@@ -943,9 +1020,9 @@ extern "C" int fib_count_nonfinite(fib_ctx* c, int var, uint64_t* count) {
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
   CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
-  const float* base = var == 0 ? c->x[c->cur] : c->s[var - 1];
+  const PlaneRef pl = plane_of(c, var);
   nonfinite_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(
-      base, c->g, var == 0 ? 1 : 0, reinterpret_cast<unsigned long long*>(c->red));
+      pl.base, c->g, pl.halo, reinterpret_cast<unsigned long long*>(c->red));
   CU(cudaGetLastError());
   c->launches++;
   unsigned long long h = 0;

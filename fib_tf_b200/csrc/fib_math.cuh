@@ -107,8 +107,11 @@ __device__ __forceinline__ float m_expm1_neg(float x) {
 
 __device__ __forceinline__ float m_log(float x) { return sfu_lg2(x) * 0.693147182464599609375f; }
 __device__ __forceinline__ float m_sqrt(float x) { return sfu_sqrt(x); }
+// 1 + e^{-2z} as ONE explicit FMA: left to the compiler, ptxas decides per kernel whether the
+// multiply and the add fuse, and two kernels that must agree bit for bit (the one- and the
+// two-steps-per-launch 4v kernels) would differ in the last place.
 __device__ __forceinline__ float m_half_1p_tanh(float z) {
-  return sfu_rcp(1.0f + m_exp(-2.0f * z));
+  return sfu_rcp(m_exp_affine(-2.0f * z, 1.0f, 1.0f));
 }
 #endif
 

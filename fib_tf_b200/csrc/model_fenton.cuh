@@ -46,17 +46,22 @@ struct Fenton4v {
     const float Hso = U > u_so ? 1.f : (U < u_so ? 0.f : 0.5f);
     const float Gso = 1.f - Hso;
 
-    const float I_fi = (-V * Hc) * (U - u_c) * (u_m - U) * (1.0f / tau_d);
-    const float I_si = (-W * S) * (1.0f / tau_si);
+    // Every multiply-add below is spelled out (fmaf / __f*_rn): whether ptxas fuses a free-standing
+    // multiply and add depends on the surrounding kernel, and the two-steps-per-launch kernel
+    // (fib_fused.cuh) must reproduce this one bit for bit.
+    const float X_fi = __fmul_rn(__fmul_rn(__fmul_rn(-V, Hc), U - u_c), u_m - U);
+    const float I_si = __fmul_rn(__fmul_rn(-W, S), 1.0f / tau_si);
     // 0.5 (a_so - tau_a) (1 + tanh z) = (a_so - tau_a) * [0.5 (1 + tanh z)]
-    const float I_so = (2.0f * c_so_half) * m_half_1p_tanh((U - b_so) * (1.0f / c_so)) +
-                       (U * Gso) * (1.0f / tau_so) + Hso * tau_a;
-    const float dU = -(I_fi + I_si + I_so);
-    const float dV = U > u_c ? -V * (1.0f / tau_vp) : (1.f - V) * (1.0f / tau_vn);
+    const float T_so = m_half_1p_tanh(__fmul_rn(U - b_so, 1.0f / c_so));
+    const float I_so = fmaf(2.0f * c_so_half, T_so,
+                            fmaf(__fmul_rn(U, Gso), 1.0f / tau_so, __fmul_rn(Hso, tau_a)));
+    // dU = -(I_fi + I_si + I_so), I_fi = X_fi / tau_d
+    const float dU = -__fadd_rn(fmaf(X_fi, 1.0f / tau_d, I_si), I_so);
+    const float dV = U > u_c ? __fmul_rn(-V, 1.0f / tau_vp) : __fmul_rn(1.f - V, 1.0f / tau_vn);
     // tau_wn1 == tau_wn2 == 75 (fenton.py:53-54): the inner tf.where is an identity
-    const float dW = U > u_c ? -W * (1.0f / tau_wp) : (1.f - W) * (1.0f / tau_wn);
+    const float dW = U > u_c ? __fmul_rn(-W, 1.0f / tau_wp) : __fmul_rn(1.f - W, 1.0f / tau_wn);
     const float r_s = fmaf(r_diff, Hc, r_sn);
-    const float dS = r_s * (m_half_1p_tanh((U - u_csi) * k_) - S);
+    const float dS = __fmul_rn(r_s, m_half_1p_tanh(__fmul_rn(U - u_csi, k_)) - S);
 
     // (U0 + dt*dU) + ddt*lap with the reference's rounding sequence (fenton.py:103): near U ~ 0 an
     // FMA's missing rounding would show up as a 1-ulp(|U0|) absolute difference

@@ -7,6 +7,8 @@ The ten unrolled explicit-Euler steps of one run() iteration (fenton.py:133-138)
 launches of the fused sm_100a kernel (boundary + 9-point Laplacian + phase term + 4v reaction),
 replayed as one CUDA graph.
 """
+import os
+
 import numpy as np
 
 from . import _capi
@@ -26,7 +28,8 @@ class Fenton4v(IonicModel):
     def define(self, s1=True):
         """Initial state U=0, V=W=1, S=0; S1 = column 1 of U set to 1 (fenton.py:116-123)."""
         super().define()
-        ctx = self._make_context()
+        self.steps_per_launch_used = self._steps_per_launch()
+        ctx = self._make_context(steps_per_launch=self.steps_per_launch_used)
         init = {'U': 0.0, 'V': 1.0, 'W': 1.0, 'S': 0.0}
         for name, val in init.items():
             a = self._local_full(val)
@@ -37,6 +40,26 @@ class Fenton4v(IonicModel):
         self._ode_op = _capi.OP_ODE
         self._State = {n: DeviceVar(self, n) for n in ctx.var_names}
         self._U = self._State['U']
+
+    # grids from this many cells up run two time steps per launch by default: below it the state
+    # (4 planes) is L2-resident and the one-step kernel is faster (2048^2: 242 vs 209 Gcell-steps/s);
+    # above it the fused kernel wins (4096^2: 195 -> 261, 8192^2: 208 -> 306)
+    FUSE_MIN_CELLS = 3072 * 3072
+
+    def _steps_per_launch(self):
+        """Temporal blocking: two time steps per kernel launch (csrc/fib_fused.cuh), BIT-IDENTICAL
+        to one step per launch.  Config key 'steps_per_launch' (1 or 2) or FIB_STEPS_PER_LAUNCH
+        override the size-based default; it needs width % 4 == 0 and no phase field, otherwise
+        one step per launch is used.  The choice depends on the global grid only, so every rank
+        of a sharded run makes the same one."""
+        want = self.__dict__.get('steps_per_launch')
+        if want is None:
+            want = os.environ.get('FIB_STEPS_PER_LAUNCH')
+        if want is None:
+            want = 2 if self.height * self.width >= self.FUSE_MIN_CELLS else 1
+        able = self.phase is None and self.width % 4 == 0 and \
+            (self._nranks == 1 or self.height // self._nranks >= 2)
+        return 2 if int(want) == 2 and able else 1
 
     def pot(self):
         return self._U

@@ -127,7 +127,7 @@ class IonicModel:
         self.phase = np.maximum(self.phase, 1e-5)
 
     # ---- device context ---------------------------------------------------------------------
-    def _make_context(self, flags=0):
+    def _make_context(self, flags=0, steps_per_launch=0):
         cfgd = self.__dict__
         device = cfgd.get('device')
         if device is None:
@@ -137,7 +137,7 @@ class IonicModel:
         sharded = self._nranks > 1
         ctx = _capi.Context(self.MODEL_ID, self.height, self.width, self.dt, self.diff, flags=flags,
                             device=device, row0=self._row0 if sharded else 0,
-                            rows=self._rows if sharded else 0)
+                            rows=self._rows if sharded else 0, steps_per_launch=steps_per_launch)
         if self.phase is not None:
             ctx.set_phase(np.asarray(self.phase, dtype=np.float32), self._phase_row0)
         if sharded:

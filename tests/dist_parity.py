@@ -25,13 +25,19 @@ def main():
     ok = True
     for kind, extra, iters in (('fenton4v', {}, 4), ('br', {'cheby': True, 'skip': True}, 5),
                                ('br', {'cheby': True, 'width': 1300, 'height': 900}, 3),
-                               ('court', {}, 12), ('court_ultra', {'ultra_slow': True}, 8)):
+                               ('court', {}, 12), ('court_ultra', {'ultra_slow': True}, 8),
+                               # two time steps per launch (two halo rows of all four planes per
+                               # exchange, no phase field) against ONE step per launch, unsharded
+                               ('fenton4v', {'steps_per_launch': 2}, 4),
+                               ('fenton4v', {'steps_per_launch': 2, 'width': 1300, 'height': 900}, 3)):
         cfg = dict(base, **extra)
+        fused = cfg.get('steps_per_launch') == 2
         models = [CLASSES[kind](dict(cfg, distributed=True, device=local))]
         if rank == 0:
-            models.append(CLASSES[kind](dict(cfg, device=local)))
+            models.append(CLASSES[kind](dict(cfg, device=local, steps_per_launch=1)))
         for m in models:
-            m.add_hole_to_phase_field(90, 60, 17)
+            if not fused:
+                m.add_hole_to_phase_field(90, 60, 17)
             m.define()
             m.add_pace_op('s2', 'luq', float(m.max_v) * 0.4)
         for i in range(iters):
@@ -49,8 +55,10 @@ def main():
                 ok &= same
                 if not same:
                     print('MISMATCH %s %s max|d|=%g' % (kind, name, np.abs(full - ref).max()))
+        if fused:
+            assert models[0]._ctx.launch_count() < 10 * iters      # really two steps per launch
         if rank == 0:
-            print('%-12s %d ranks: sharded == unsharded: %s' % (kind, world, ok), flush=True)
+            print('%-12s %s %d ranks: sharded == unsharded: %s' % (kind, extra, world, ok), flush=True)
         for m in models:
             m.close()
     flag = torch.tensor([1 if ok else 0], device='cuda')

@@ -48,6 +48,9 @@ def _cfg(**kw):
     (dict(height=2), 'too small'),
     (dict(dt=0.0), 'dt must be'),
     (dict(steps_per_launch=3), 'steps_per_launch'),
+    (dict(steps_per_launch=2, model=1), 'steps_per_launch=2 needs'),       # 4v only
+    (dict(steps_per_launch=2, width=66), 'steps_per_launch=2 needs'),      # width % 4
+    (dict(steps_per_launch=2, row0=10, rows=1), 'at least 2 rows'),
     (dict(row0=10, rows=10), 'outside the grid'),
     (dict(height=70000, width=40000), '2^31'),      # 32-bit element offsets: shard the grid instead
 ])

@@ -642,3 +642,57 @@ def test_courtemanche_removable_singularities(cuda):
         e = onp.rel_err(gpu.state[g][inner], exact[inner], onp.var_floor('court_ultra', g))
         assert e <= 2e-5, (g, e)
     gpu.close()
+
+
+@pytest.mark.parametrize('H,W,nshards', [(3, 4, 1), (7, 8, 1), (45, 72, 4), (64, 128, 2), (130, 244, 3),
+                                         (300, 500, 1), (1000, 1100, 4)])
+def test_two_steps_per_launch_is_bit_identical(cuda, H, W, nshards):
+    """Temporal blocking (csrc/fib_fused.cuh): steps_per_launch=2 must reproduce the one-step
+    kernels BIT FOR BIT -- unsharded (CUDA-graph replay and direct launches) and as row shards
+    exchanging two halo rows of all four planes -- from a random state (non-trivial border ring),
+    with a stimulus crossing the seams half way."""
+    from fib_tf_b200 import _capi
+    from fib_tf_b200.sharding import partition_rows
+    dt, diff = 0.1, 1.5
+    rng = np.random.default_rng(H * 1000 + W)
+    init = {'U': rng.uniform(0.0, 1.0, (H, W)), 'V': rng.uniform(0.0, 1.0, (H, W)),
+            'W': rng.uniform(0.0, 1.0, (H, W)), 'S': rng.uniform(0.0, 1.0, (H, W))}
+    init = {k: v.astype(np.float32) for k, v in init.items()}
+    init['U'][H // 3:H // 2 + 1, W // 4:W // 2] = 0.95          # a depolarised patch
+
+    def make(steps_per_launch, flags=0, parts=((0, 0),)):
+        out = [_capi.Context(_capi.FENTON4V, H, W, dt, diff, flags=flags, row0=r0, rows=n,
+                             steps_per_launch=steps_per_launch) for r0, n in parts]
+        for s, (r0, n) in zip(out, parts):
+            for v, a in init.items():
+                s.set_state(v, a if n == 0 else a[r0:r0 + n])
+        return out
+
+    stim = ('U', 1, max(H - 1, 2), 1, max(W // 2, 2), 0.6, 0.0)
+    ref, = make(1)
+    fused, = make(2)
+    direct, = make(2, flags=_capi.F_NO_GRAPH)
+    parts = [p for p in partition_rows(H, nshards)]
+    shards = make(2, flags=_capi.F_NO_GRAPH, parts=parts) if nshards > 1 else []
+    for it in range(4):
+        for c in (ref, fused, direct):
+            c.step(_capi.OP_ODE, 1)
+        if shards:
+            _capi.step_group(shards, _capi.OP_ODE, 1)
+        if it == 1:
+            for c in [ref, fused, direct] + shards:
+                c.stimulate(*stim)
+    for v in ref.var_names:
+        want = ref.get_state(v)
+        assert np.isfinite(want).all()
+        assert np.array_equal(fused.get_state(v), want), 'graph replay, %s' % v
+        assert np.array_equal(direct.get_state(v), want), 'direct launches, %s' % v
+        if shards:
+            got = np.concatenate([s.get_state(v) for s in shards], axis=0)
+            assert np.array_equal(got, want), 'row shards, %s' % v
+    # probes and reductions read the fused layout correctly
+    assert fused.probe('W', H // 2, W // 2) == ref.probe('W', H // 2, W // 2)
+    a, b = fused.weighted_sum('V'), ref.weighted_sum('V')
+    assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) and a[1] == b[1]
+    for c in [ref, fused, direct] + shards:
+        c.close()
