@@ -56,7 +56,8 @@ def main():
                 if not same:
                     print('MISMATCH %s %s max|d|=%g' % (kind, name, np.abs(full - ref).max()))
         if fused:
-            assert models[0]._ctx.launch_count() < 10 * iters      # really two steps per launch
+            # really two steps per launch: 5 x (top rows, bottom rows, interior) per iteration, not 10 x
+            assert models[0]._ctx.launch_count() < 20 * iters, models[0]._ctx.launch_count()
         if rank == 0:
             print('%-12s %s %d ranks: sharded == unsharded: %s' % (kind, extra, world, ok), flush=True)
         for m in models:
