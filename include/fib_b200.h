@@ -70,8 +70,10 @@ typedef struct {
   uint32_t flags;            /* FIB_F_*                                                              */
   int32_t  device;           /* CUDA device ordinal                                                  */
   int32_t  row0, rows;       /* this shard = global rows [row0, row0+rows); rows == 0 -> whole grid   */
-  int32_t  steps_per_launch; /* temporal blocking: time steps fused per kernel launch (0/1 = off);
-                                must divide dt_per_step                           */
+  int32_t  steps_per_launch; /* temporal blocking: time steps per kernel launch.  0/1 = one; 2 = two
+                                (Fenton 4v only, width % 4 == 0, no phase field; results are
+                                bit-identical to one step per launch; shards exchange two halo rows
+                                of every plane per launch).  Must divide dt_per_step */
   int32_t  reserved[6];
 } fib_config;
 

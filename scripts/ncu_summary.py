@@ -31,8 +31,10 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 CELLS = 4096 * 4096
 traffic = {}
 lines = []
-for rep, key, balg in (('prof_4v', 'fenton4v_step', 32), ('prof_br', 'br_cheby_step', 64), ('prof_br_exact', 'br_exact_step', 64),
-                       ('prof_court', 'court_ultra_step', 168)):
+# (report, key in traffic.json, algorithmic bytes per cell-step, time steps per launch)
+for rep, key, balg, spl in (('prof_4v', 'fenton4v_step', 32, 1), ('prof_4v_fused', 'fenton4v_fused2_step', 32, 2),
+                            ('prof_br', 'br_cheby_step', 64, 1), ('prof_br_exact', 'br_exact_step', 64, 1),
+                            ('prof_court', 'court_ultra_step', 168, 1)):
     path = os.path.join(G, rep + '.ncu-rep')
     if not os.path.exists(path):
         continue
@@ -40,8 +42,8 @@ for rep, key, balg in (('prof_4v', 'fenton4v_step', 32), ('prof_br', 'br_cheby_s
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, r = rows[0], rows[1], rows[2]
     d = {h: (r[i], units[i]) for i, h in enumerate(hdr)}
-    lines.append('== %s : %s   (4096x4096 grid, one launch = one time step, ncu --set full --clock-control none)'
-                 % (rep, d['Kernel Name'][0]))
+    lines.append('== %s : %s   (4096x4096 grid, one launch = %s, ncu --set full --clock-control none)'
+                 % (rep, d['Kernel Name'][0], 'one time step' if spl == 1 else '%d time steps' % spl))
     for k in KEEP:
         if k in d:
             lines.append('   %-86s %s %s' % (k, d[k][0], d[k][1]))
@@ -51,11 +53,12 @@ for rep, key, balg in (('prof_4v', 'fenton4v_step', 32), ('prof_br', 'br_cheby_s
         v = float(v.replace(',', ''))
         return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9,
                     'inst': 1}.get(u, 1)
-    dram = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
-    inst = num('smsp__inst_executed.sum') * 32 / CELLS
-    t = num('gpu__time_duration.sum')
+    # per CELL-STEP: a launch of the fused kernel advances every cell by `spl` steps
+    dram = (num('dram__bytes_read.sum') + num('dram__bytes_write.sum')) / spl
+    inst = num('smsp__inst_executed.sum') * 32 / CELLS / spl
+    t = num('gpu__time_duration.sum') / spl
     traffic[key] = {'dram_bytes_per_cell': dram / CELLS, 'algorithmic_bytes_per_cell': balg,
-                    'thread_instructions_per_cell': inst, 'ncu_duration_us': t * 1e6,
+                    'thread_instructions_per_cell': inst, 'ncu_duration_us': t * 1e6, 'time_steps_per_launch': spl,
                     'gcell_steps_per_s_under_ncu': CELLS / t / 1e9, 'source': 'profiles/%s_ncu_summary.txt' % tag}
     lines.append('   -> DRAM bytes / cell-step %.1f (algorithmic %d), thread-instructions / cell-step %.0f, '
                  '%.1f Gcell-steps/s under ncu (cold cache, serialised)' % (dram / CELLS, balg, inst, CELLS / t / 1e9))
@@ -70,7 +73,7 @@ if os.path.exists(lp):
             agg[r[4]][1] += float(r[-1])
     tot = sum(v[1] for v in agg.values())
     lines.append('== launch list of `python bench.py --size 4096 --steps 2 --warmup 3 --no-cpu` '
-                 '(ncu --metrics gpu__time_duration.sum --launch-skip 4031 --launch-count 60: the warm-up tail, the timed '
+                 '(ncu --metrics gpu__time_duration.sum --launch-skip 4011 --launch-count 60: the warm-up tail, the timed '
                  'region and the e2e loop, after the 4000 launches that build the 512^2 spiral tile; shares, not absolutes)')
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append('   %5.1f %%  %4d launches  %9.1f us avg   %s' % (100 * ns / tot, n, ns / n / 1e3, k[:90]))
