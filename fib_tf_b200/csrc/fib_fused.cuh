@@ -45,6 +45,12 @@ struct Fused2Args {
 #ifndef FIB_FUSE_PREFETCH
 #define FIB_FUSE_PREFETCH 1
 #endif
+#ifndef FIB_FUSE_UNROLL
+#define FIB_FUSE_UNROLL 1
+#endif
+#ifndef FIB_FUSE_BY
+#define FIB_FUSE_BY 4      // warps (row blocks) per CTA
+#endif
 #ifndef FIB_FUSE_PFD
 #define FIB_FUSE_PFD 1      // prefetch distance in rows
 #endif
@@ -55,7 +61,7 @@ __device__ __forceinline__ float pick4(const float (&v)[4], int i) {
   return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
 }
 
-__global__ void __launch_bounds__(kBX * 4, FIB_FUSE_MINB)
+__global__ void __launch_bounds__(kBX * FIB_FUSE_BY, FIB_FUSE_MINB * 4 / FIB_FUSE_BY)
 fenton_fused2_kernel(const Geom g, const Fused2Args a) {
   const int lane = threadIdx.x;
   const int c = blockIdx.x * kFuseCols - 4 + lane * 4;        // first of my four columns
@@ -88,7 +94,11 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
   load_enforced_row<4>(a.in[0], xrow(j - 1), cw, W, xN);
   load_enforced_row<4>(a.in[0], xrow(j), cw, W, xC);
 
+#if FIB_FUSE_UNROLL == 2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
   for (; j <= g1; ++j) {
     // ---------------- step 1 on row j ----------------
     load_enforced_row<4>(a.in[0], xrow(j + 1), cw, W, xS);
@@ -197,12 +207,13 @@ inline cudaError_t launch_fused2(const Geom& g, Fused2Args a, cudaStream_t st, i
   if (a.nrows <= 0) return cudaSuccess;
   const long nseg = (g.W + kFuseCols - 1) / kFuseCols;
   static const int force = getenv("FIB_FUSE_R") ? atoi(getenv("FIB_FUSE_R")) : 0;   // experiments
-  auto ctas = [&](int R) { return nseg * (((a.nrows + R - 1) / R + 3) / 4); };
+  constexpr int BY = FIB_FUSE_BY;
+  auto ctas = [&](int R) { return nseg * (((a.nrows + R - 1) / R + BY - 1) / BY); };
   int R = 8;
   if (force > 0) {
     R = force;
   } else {
-    const long slots = (long)sms * FIB_FUSE_MINB;
+    const long slots = (long)sms * (FIB_FUSE_MINB * 4 / BY);
     long best = -1;
     for (int r = 8; r <= 48; ++r) {
       const long waves = (ctas(r) + slots - 1) / slots;
@@ -211,7 +222,7 @@ inline cudaError_t launch_fused2(const Geom& g, Fused2Args a, cudaStream_t st, i
     }
   }
   a.R = R;
-  dim3 block(kBX, 4), grid((unsigned)nseg, (unsigned)(((a.nrows + R - 1) / R + 3) / 4));
+  dim3 block(kBX, BY), grid((unsigned)nseg, (unsigned)(((a.nrows + R - 1) / R + BY - 1) / BY));
   fenton_fused2_kernel<<<grid, block, 0, st>>>(g, a);
   return cudaGetLastError();
 }
