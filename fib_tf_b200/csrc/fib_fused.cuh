@@ -54,9 +54,6 @@ struct Fused2Args {
 #ifndef FIB_FUSE_PFD
 #define FIB_FUSE_PFD 1      // prefetch distance in rows
 #endif
-__device__ __forceinline__ void prefetch_l1(const float* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 __device__ __forceinline__ float pick4(const float (&v)[4], int i) {
   return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
 }

@@ -183,6 +183,7 @@ struct BeelerReuter {
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
       SLOW ? (CHEBY ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
+  static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
   static constexpr bool NEED_LAP = true;
   static constexpr bool STORE_X = true;
