@@ -121,6 +121,8 @@ struct fib_ctx {
   float* phase = nullptr;             // halo layout
   unsigned char* pmask = nullptr;     // [rows][pmask_pitch] non-trivial-phase flags per 32 columns
   int pmask_pitch = 0;
+  float* phase2 = nullptr;            // fuse == 2: second copy of phi with kFuseHalo halo rows ...
+  unsigned char* pmask2 = nullptr;    // ... and its flags for local rows -1 .. rows: [rows + 2][pmask_pitch]
   float* lut = nullptr;               // 150 x 30, the ABI layout (courtemanche.h order)
   float* lut_t = nullptr;             // 30 x 160 transposed copy the kernels read
   bool have_lut = false, have_cheb = false, halo_dirty = true, comm_pending = false;
@@ -180,6 +182,27 @@ __global__ void phase_mask_kernel(const float* __restrict__ phase, Geom g, unsig
       for (int c = c0; c <= c1; ++c) same &= (phase[(size_t)rr * g.pitch + c] == first);
     }
     mask[(size_t)lr * mpitch + b] = same ? 0 : 1;
+  }
+}
+
+// the same flags for the two-steps-per-launch layout: phi with kFuseHalo halo rows, local rows
+// -1 .. rows (the first step is recomputed on the neighbours' edge rows); rows outside the grid: 0
+__global__ void phase_mask2_kernel(const float* __restrict__ phase, Geom g, unsigned char* __restrict__ mask,
+                                   int mpitch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= mpitch) return;
+  const int c0 = max(b * 32 - 1, 0), c1 = min(b * 32 + 32, g.W - 1);
+  for (int lr = (int)blockIdx.y - 1; lr <= g.rows; lr += gridDim.y) {
+    const int gr = g.row0 + lr;
+    bool same = true;
+    if (gr >= 0 && gr < g.H) {
+      const float first = phase[(size_t)(lr + kFuseHalo) * g.pitch + c0];
+      for (int dr = -1; dr <= 1; ++dr) {
+        const int rr = reflecti(gr + dr, g.H) - g.row0 + kFuseHalo;
+        for (int c = c0; c <= c1; ++c) same &= (phase[(size_t)rr * g.pitch + c] == first);
+      }
+    }
+    mask[(size_t)(lr + 1) * mpitch + b] = same ? 0 : 1;
   }
 }
 
@@ -361,6 +384,8 @@ extern "C" int fib_destroy(fib_ctx* c) {
   for (int k = 0; k < S_COUNT; ++k) cudaFree(c->s[k]);
   cudaFree(c->phase);
   cudaFree(c->pmask);
+  cudaFree(c->phase2);
+  cudaFree(c->pmask2);
   cudaFree(c->lut);
   cudaFree(c->lut_t);
   cudaFree(c->red);
@@ -487,8 +512,6 @@ extern "C" int fib_set_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1,
 
 extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
-  if (c->fuse == 2 && rows_host)
-    return fail(FIB_E_STATE, "a phase field is not available with steps_per_launch=2");
   DevGuard dg(c->cfg.device);
   CU(cudaStreamSynchronize(c->stream));
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);   // graphs bake the phase pointer in
@@ -496,11 +519,17 @@ extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, 
   if (!rows_host) {
     CU(cudaFree(c->phase));
     CU(cudaFree(c->pmask));
+    CU(cudaFree(c->phase2));
+    CU(cudaFree(c->pmask2));
     c->phase = nullptr;
     c->pmask = nullptr;
+    c->phase2 = nullptr;
+    c->pmask2 = nullptr;
     return 0;
   }
-  const int need0 = max(c->g.row0 - 1, 0), need1 = min(c->g.row0 + c->g.rows + 1, c->g.H);
+  // one halo row of phi for one step per launch, kFuseHalo for two
+  const int hr = c->fuse == 2 ? kFuseHalo : 1;
+  const int need0 = max(c->g.row0 - hr, 0), need1 = min(c->g.row0 + c->g.rows + hr, c->g.H);
   if (first_row > need0 || first_row + nrows < need1)
     return fail(FIB_E_ARG, "phase rows [%d,%d) do not cover [%d,%d)", first_row, first_row + nrows,
                 need0, need1);
@@ -508,16 +537,37 @@ extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, 
     CU(cudaMalloc(&c->phase, c->halo_floats() * sizeof(float)));
     CU(cudaMemsetAsync(c->phase, 0, c->halo_floats() * sizeof(float), c->stream));
   }
-  // device row (need0 - row0 + 1) <- host row (need0 - first_row)
-  CU(cudaMemcpy2DAsync(c->phase + (size_t)(need0 - c->g.row0 + 1) * c->g.pitch,
-                       c->g.pitch * sizeof(float),
-                       rows_host + (size_t)(need0 - first_row) * c->g.W, c->g.W * sizeof(float),
-                       c->g.W * sizeof(float), need1 - need0, cudaMemcpyHostToDevice, c->stream));
+  // device row (n0 - row0 + 1) <- host row (n0 - first_row); this copy (one halo row) also serves
+  // the reductions (fib_weighted_sum)
+  {
+    const int n0 = max(c->g.row0 - 1, 0), n1 = min(c->g.row0 + c->g.rows + 1, c->g.H);
+    CU(cudaMemcpy2DAsync(c->phase + (size_t)(n0 - c->g.row0 + 1) * c->g.pitch,
+                         c->g.pitch * sizeof(float),
+                         rows_host + (size_t)(n0 - first_row) * c->g.W, c->g.W * sizeof(float),
+                         c->g.W * sizeof(float), n1 - n0, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (c->fuse == 2) {
+    if (!c->phase2) {
+      CU(cudaMalloc(&c->phase2, c->fused_floats() * sizeof(float)));
+      CU(cudaMemsetAsync(c->phase2, 0, c->fused_floats() * sizeof(float), c->stream));
+    }
+    CU(cudaMemcpy2DAsync(c->phase2 + (size_t)(need0 - c->g.row0 + kFuseHalo) * c->g.pitch,
+                         c->g.pitch * sizeof(float),
+                         rows_host + (size_t)(need0 - first_row) * c->g.W, c->g.W * sizeof(float),
+                         c->g.W * sizeof(float), need1 - need0, cudaMemcpyHostToDevice, c->stream));
+  }
   c->pmask_pitch = (c->g.W + 31) / 32;
   if (!c->pmask) CU(cudaMalloc(&c->pmask, (size_t)c->g.rows * c->pmask_pitch));
   {
     dim3 block(64), grid((c->pmask_pitch + 63) / 64, min(c->g.rows, 65535));
     phase_mask_kernel<<<grid, block, 0, c->stream>>>(c->phase, c->g, c->pmask, c->pmask_pitch);
+    CU(cudaGetLastError());
+    c->launches++;
+  }
+  if (c->fuse == 2) {
+    if (!c->pmask2) CU(cudaMalloc(&c->pmask2, (size_t)(c->g.rows + 2) * c->pmask_pitch));
+    dim3 block(64), grid((c->pmask_pitch + 63) / 64, min(c->g.rows + 2, 65535));
+    phase_mask2_kernel<<<grid, block, 0, c->stream>>>(c->phase2, c->g, c->pmask2, c->pmask_pitch);
     CU(cudaGetLastError());
     c->launches++;
   }
@@ -659,6 +709,9 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
       if (c->fuse == 2) {                       // time steps `sub` and `sub + 1` in one launch
         Fused2Args f;
         for (int v = 0; v < 4; ++v) { f.in[v] = c->fx[c->cur][v]; f.out[v] = c->fx[c->cur ^ 1][v]; }
+        f.phase = c->phase2;
+        f.pmask = c->pmask2;
+        f.pmask_pitch = c->pmask_pitch;
         f.lr0 = lr0;
         f.nrows = nrows;
         f.R = 0;

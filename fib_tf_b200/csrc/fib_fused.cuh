@@ -21,7 +21,8 @@
 // Boundary (fib_stencil.cuh): step 2 sees U1 through the same index map as step 1 sees U,
 //   Xp[r][c] = U1[clamp(r,1,H-2)][clamp(c,1,W-2)]; the column clamp is applied when the window is
 // formed, the row clamp when the three window rows are picked.
-// Restrictions: W % 4 == 0, no phase field (fib_create / fib_set_phase reject the combination).
+// The phase field is read like in step_kernel (on demand, where fib_set_phase flagged the block),
+// from a copy of phi in the same two-halo-row layout.  Restriction: W % 4 == 0 (fib_create).
 #pragma once
 #include "model_fenton.cuh"
 
@@ -37,6 +38,9 @@ constexpr int kFuseCols = 120;   // output columns per warp: lanes 1..30 x 4 cel
 struct Fused2Args {
   const float* in[4];   // U, V, W, S at time t   (halo layout, kFuseHalo rows above and below)
   float* out[4];        // the same at time t + 2 dt
+  const float* phase;   // phi in the SAME halo layout (kFuseHalo rows), or nullptr
+  const unsigned char* pmask;   // [rows + 2][pmask_pitch], local rows -1 .. rows: 1 where the phase term
+  int pmask_pitch;              //   of a 32-column block can be non-zero (fib_set_phase)
   int lr0, nrows;       // local OUTPUT row range of this launch
   int R;                // output rows per warp
   Fenton4v::Params p;
@@ -58,7 +62,9 @@ __device__ __forceinline__ float pick4(const float (&v)[4], int i) {
   return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
 }
 
-__global__ void __launch_bounds__(kBX * FIB_FUSE_BY, FIB_FUSE_MINB * 4 / FIB_FUSE_BY)
+// the phase-field flavour needs ~20 more registers for the phi windows: one CTA per SM fewer
+template <bool PHASE>
+__global__ void __launch_bounds__(kBX * FIB_FUSE_BY, (FIB_FUSE_MINB - (PHASE ? 1 : 0)) * 4 / FIB_FUSE_BY)
 fenton_fused2_kernel(const Geom g, const Fused2Args a) {
   const int lane = threadIdx.x;
   const int c = blockIdx.x * kFuseCols - 4 + lane * 4;        // first of my four columns
@@ -73,6 +79,15 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
   const ColWindow<4> cw(cs, W);
   auto rowoff = [&](int gr) { return (gr - g.row0 + kFuseHalo) * pitch; };
   auto xrow = [&](int gr) { return rowoff(clampi(gr, 1, H - 2)); };
+  auto prow = [&](int gr) { return rowoff(reflecti(gr, H)); };
+  // the phase term of row gr (ionic.py:70-81), exactly as step_kernel forms it: phi is fetched
+  // on demand, only where fib_set_phase flagged the 32-column block
+  auto phase_flag = [&](int gr) { return a.pmask[(gr - g.row0 + 1) * a.pmask_pitch + (cs >> 5)] != 0; };
+  auto load_phi = [&](int gr, float (&pN)[4], float (&pS)[4], float (&pC)[6]) {
+    VecIO<4>::ld(a.phase + (prow(gr - 1) + cs), pN);
+    VecIO<4>::ld(a.phase + (prow(gr + 1) + cs), pS);
+    load_reflect_row<4>(a.phase, prow(gr), cw, W, pC);
+  };
   StepArgs<Fenton4v> sa;
   sa.p = a.p;
 
@@ -121,10 +136,19 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) VecIO<4>::ld(a.in[k + 1] + off, sQ[k]);
+      float pN[4], pS[4], pC[6];
+      bool ph = false;
+      if (PHASE) {
+        ph = phase_flag(j);
+        if (ph) load_phi(j, pN, pS, pC);
+      }
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
-        const float lap = lap9(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], xN[l], xS[l], xN[l + 2],
-                               xS[l + 2], xC[l + 1]);
+        float lap = lap9(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], xN[l], xS[l], xN[l + 2],
+                         xS[l + 2], xC[l + 1]);
+        if (PHASE && ph)
+          lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l], pS[l],
+                                          pC[l], pC[l + 2], pC[l + 1]));
         float sl[3] = {sQ[0][l], sQ[1][l], sQ[2][l]};
         Fenton4v::cell(sa, xraw[l], xC[l + 1], lap, sl, u1[l]);
         sQ[0][l] = sl[0]; sQ[1][l] = sl[1]; sQ[2][l] = sl[2];
@@ -165,11 +189,20 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
           nS[q] = iS == 0 ? wA[q] : (iS == 1 ? wB[q] : wC[q]);
         }
       }
+      float pN[4], pS[4], pC[6];
+      bool ph = false;
+      if (PHASE) {
+        ph = phase_flag(r);
+        if (ph) load_phi(r, pN, pS, pC);
+      }
       float u2[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
-        const float lap = lap9(nN[l + 1], nS[l + 1], nC[l], nC[l + 2], nN[l], nS[l], nN[l + 2],
-                               nS[l + 2], nC[l + 1]);
+        float lap = lap9(nN[l + 1], nS[l + 1], nC[l], nC[l + 2], nN[l], nS[l], nN[l + 2],
+                         nS[l + 2], nC[l + 1]);
+        if (PHASE && ph)
+          lap = __fadd_rn(lap, phase_term(nN[l + 1], nS[l + 1], nC[l], nC[l + 2], pN[l], pS[l],
+                                          pC[l], pC[l + 2], pC[l + 1]));
         const float raw = l == 0 ? eB[0] : (l == 3 ? eB[1] : wB[l + 1]);
         float sl[3] = {sP[0][l], sP[1][l], sP[2][l]};
         Fenton4v::cell(sa, raw, nC[l + 1], lap, sl, u2[l]);
@@ -210,7 +243,7 @@ inline cudaError_t launch_fused2(const Geom& g, Fused2Args a, cudaStream_t st, i
   if (force > 0) {
     R = force;
   } else {
-    const long slots = (long)sms * (FIB_FUSE_MINB * 4 / BY);
+    const long slots = (long)sms * ((FIB_FUSE_MINB - (a.phase ? 1 : 0)) * 4 / BY);
     long best = -1;
     for (int r = 8; r <= 48; ++r) {
       const long waves = (ctas(r) + slots - 1) / slots;
@@ -220,7 +253,8 @@ inline cudaError_t launch_fused2(const Geom& g, Fused2Args a, cudaStream_t st, i
   }
   a.R = R;
   dim3 block(kBX, BY), grid((unsigned)nseg, (unsigned)(((a.nrows + R - 1) / R + BY - 1) / BY));
-  fenton_fused2_kernel<<<grid, block, 0, st>>>(g, a);
+  if (a.phase) fenton_fused2_kernel<true><<<grid, block, 0, st>>>(g, a);
+  else fenton_fused2_kernel<false><<<grid, block, 0, st>>>(g, a);
   return cudaGetLastError();
 }
 

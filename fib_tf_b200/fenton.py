@@ -45,19 +45,23 @@ class Fenton4v(IonicModel):
     # (4 planes) is L2-resident and the one-step kernel is faster (2048^2: 242 vs 209 Gcell-steps/s);
     # above it the fused kernel wins (4096^2: 195 -> 261, 8192^2: 208 -> 306)
     FUSE_MIN_CELLS = 3072 * 3072
+    # with a phase field the fused kernel runs one CTA per SM fewer (phi windows): 3072^2 is a tie
+    # (175 vs 178), 4096^2 185 -> 204, 8192^2 198 -> 240
+    FUSE_MIN_CELLS_PHASE = 4096 * 4096
 
     def _steps_per_launch(self):
         """Temporal blocking: two time steps per kernel launch (csrc/fib_fused.cuh), BIT-IDENTICAL
         to one step per launch.  Config key 'steps_per_launch' (1 or 2) or FIB_STEPS_PER_LAUNCH
-        override the size-based default; it needs width % 4 == 0 and no phase field, otherwise
-        one step per launch is used.  The choice depends on the global grid only, so every rank
+        override the size-based default; it needs width % 4 == 0, otherwise one step per launch
+        is used.  The choice depends on the global grid only, so every rank
         of a sharded run makes the same one."""
         want = self.__dict__.get('steps_per_launch')
         if want is None:
             want = os.environ.get('FIB_STEPS_PER_LAUNCH')
         if want is None:
-            want = 2 if self.height * self.width >= self.FUSE_MIN_CELLS else 1
-        able = self.phase is None and self.width % 4 == 0 and \
+            floor = self.FUSE_MIN_CELLS if self.phase is None else self.FUSE_MIN_CELLS_PHASE
+            want = 2 if self.height * self.width >= floor else 1
+        able = self.width % 4 == 0 and \
             (self._nranks == 1 or self.height // self._nranks >= 2)
         return 2 if int(want) == 2 and able else 1
 

@@ -86,8 +86,9 @@ class IonicModel:
         parts = partition_rows(self.height, self._nranks)
         self._row0, self._rows = parts[self._rank]
         # host copy of the phase field covers these global rows (everything when not sharded)
-        self._phase_row0 = max(self._row0 - 1, 0)
-        self._phase_row1 = min(self._row0 + self._rows + 1, self.height)
+        # (two halo rows: what the two-steps-per-launch kernel needs; one would do otherwise)
+        self._phase_row0 = max(self._row0 - 2, 0)
+        self._phase_row1 = min(self._row0 + self._rows + 2, self.height)
 
     # ---- the reference's graph-building helpers have no meaning without TensorFlow ----------
     def _no_graph(self, name):

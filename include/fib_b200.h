@@ -71,7 +71,7 @@ typedef struct {
   int32_t  device;           /* CUDA device ordinal                                                  */
   int32_t  row0, rows;       /* this shard = global rows [row0, row0+rows); rows == 0 -> whole grid   */
   int32_t  steps_per_launch; /* temporal blocking: time steps per kernel launch.  0/1 = one; 2 = two
-                                (Fenton 4v only, width % 4 == 0, no phase field; results are
+                                (Fenton 4v only, width % 4 == 0; results are
                                 bit-identical to one step per launch; shards exchange two halo rows
                                 of every plane per launch).  Must divide dt_per_step */
   int32_t  reserved[6];

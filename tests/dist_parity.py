@@ -27,16 +27,18 @@ def main():
                                ('br', {'cheby': True, 'width': 1300, 'height': 900}, 3),
                                ('court', {}, 12), ('court_ultra', {'ultra_slow': True}, 8),
                                # two time steps per launch (two halo rows of all four planes per
-                               # exchange, no phase field) against ONE step per launch, unsharded
-                               ('fenton4v', {'steps_per_launch': 2}, 4),
+                               # exchange) against ONE step per launch, unsharded; without and
+                               # with a phase field
+                               ('fenton4v', {'steps_per_launch': 2, 'hole': False}, 4),
                                ('fenton4v', {'steps_per_launch': 2, 'width': 1300, 'height': 900}, 3)):
         cfg = dict(base, **extra)
+        hole = cfg.pop('hole', True)
         fused = cfg.get('steps_per_launch') == 2
         models = [CLASSES[kind](dict(cfg, distributed=True, device=local))]
         if rank == 0:
             models.append(CLASSES[kind](dict(cfg, device=local, steps_per_launch=1)))
         for m in models:
-            if not fused:
+            if hole:
                 m.add_hole_to_phase_field(90, 60, 17)
             m.define()
             m.add_pace_op('s2', 'luq', float(m.max_v) * 0.4)

@@ -644,13 +644,15 @@ def test_courtemanche_removable_singularities(cuda):
     gpu.close()
 
 
+@pytest.mark.parametrize('hole', [False, True])
 @pytest.mark.parametrize('H,W,nshards', [(3, 4, 1), (7, 8, 1), (45, 72, 4), (64, 128, 2), (130, 244, 3),
                                          (300, 500, 1), (1000, 1100, 4)])
-def test_two_steps_per_launch_is_bit_identical(cuda, H, W, nshards):
+def test_two_steps_per_launch_is_bit_identical(cuda, H, W, nshards, hole):
     """Temporal blocking (csrc/fib_fused.cuh): steps_per_launch=2 must reproduce the one-step
     kernels BIT FOR BIT -- unsharded (CUDA-graph replay and direct launches) and as row shards
     exchanging two halo rows of all four planes -- from a random state (non-trivial border ring),
-    with a stimulus crossing the seams half way."""
+    with a stimulus crossing the seams half way, without and with a phase field (two holes, one of
+    them across a shard seam and one touching the border)."""
     from fib_tf_b200 import _capi
     from fib_tf_b200.sharding import partition_rows
     dt, diff = 0.1, 1.5
@@ -660,12 +662,22 @@ def test_two_steps_per_launch_is_bit_identical(cuda, H, W, nshards):
     init = {k: v.astype(np.float32) for k, v in init.items()}
     init['U'][H // 3:H // 2 + 1, W // 4:W // 2] = 0.95          # a depolarised patch
 
+    phase = None
+    if hole:
+        yy, xx = np.mgrid[0:H, 0:W]
+        phase = np.ones((H, W))
+        for cy, cx, rad in ((H / 2.0, W / 2.0, max(min(H, W) / 6.0, 1.0)), (0.0, W * 0.8, max(min(H, W) / 8.0, 1.0))):
+            phase *= 0.5 * (np.tanh(0.1 * (np.hypot(yy - cy, xx - cx) - rad) * 10.0) + 1.0)
+        phase = np.maximum(phase, 1e-5).astype(np.float32)          # ionic.py:104-105
+
     def make(steps_per_launch, flags=0, parts=((0, 0),)):
         out = [_capi.Context(_capi.FENTON4V, H, W, dt, diff, flags=flags, row0=r0, rows=n,
                              steps_per_launch=steps_per_launch) for r0, n in parts]
         for s, (r0, n) in zip(out, parts):
             for v, a in init.items():
                 s.set_state(v, a if n == 0 else a[r0:r0 + n])
+            if phase is not None:
+                s.set_phase(phase, 0)
         return out
 
     stim = ('U', 1, max(H - 1, 2), 1, max(W // 2, 2), 0.6, 0.0)
@@ -693,6 +705,7 @@ def test_two_steps_per_launch_is_bit_identical(cuda, H, W, nshards):
     # probes and reductions read the fused layout correctly
     assert fused.probe('W', H // 2, W // 2) == ref.probe('W', H // 2, W // 2)
     a, b = fused.weighted_sum('V'), ref.weighted_sum('V')
-    assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) and a[1] == b[1]
+    # (double-precision atomics: the summation order, hence the last bits, vary from run to run)
+    assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-9 * abs(b[1])
     for c in [ref, fused, direct] + shards:
         c.close()

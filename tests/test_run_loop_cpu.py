@@ -153,9 +153,9 @@ def test_courtemanche_slow_op_state_dict_and_timeline(recording, tmp_path):
 
 
 def test_steps_per_launch_choice(recording, monkeypatch):
-    """Fenton4v._steps_per_launch: two time steps per launch from 3072^2 cells up, never with a
-    phase field or a width that is not a multiple of 4; the config key and FIB_STEPS_PER_LAUNCH
-    override the size rule (but not the restrictions)."""
+    """Fenton4v._steps_per_launch: two time steps per launch from 3072^2 cells up (with or without
+    a phase field), never with a width that is not a multiple of 4; the config key and
+    FIB_STEPS_PER_LAUNCH override the size rule (but not the restriction)."""
     monkeypatch.delenv('FIB_STEPS_PER_LAUNCH', raising=False)
     base = {'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 1, 'timeline': False,
             'timeline_name': 'x', 'save_graph': False}
@@ -169,12 +169,12 @@ def test_steps_per_launch_choice(recording, monkeypatch):
     assert choice(512, 512) == 1
     assert choice(4096, 4096) == 2
     assert choice(3072, 3072) == 2 and choice(3072, 3068) == 1
-    assert choice(4096, 4096, hole=True) == 1
+    assert choice(4096, 4096, hole=True) == 2 and choice(3072, 3072, hole=True) == 1
     assert choice(4098, 4096) == 1                                   # width % 4
     assert choice(4096, 4096, steps_per_launch=1) == 1
     assert choice(512, 512, steps_per_launch=2) == 2
     monkeypatch.setenv('FIB_STEPS_PER_LAUNCH', '1')
     assert choice(4096, 4096) == 1
     monkeypatch.setenv('FIB_STEPS_PER_LAUNCH', '2')
-    assert choice(512, 512) == 2 and choice(512, 512, hole=True) == 1
+    assert choice(512, 512) == 2 and choice(512, 512, hole=True) == 2 and choice(514, 512) == 1
     assert choice(512, 512, steps_per_launch=1) == 1                 # the config key wins over the env
