@@ -128,7 +128,8 @@ int fib_snapshot_wait(fib_ctx *ctx);
 
 /* ---- phase field: replaces self.phi = tf.Variable(self.phase) (ionic.py:55-58) ---------
  * `rows_host` holds global rows [first_row, first_row+nrows) of the [H][W] phase field and must
- * cover this shard plus one row either side (clipped to the grid).  NULL removes the field. */
+ * cover this shard plus one row either side -- two rows with steps_per_launch = 2 -- clipped to the
+ * grid (passing the whole field with first_row = 0 always works).  NULL removes the field. */
 int fib_set_phase(fib_ctx *ctx, const float *rows_host, int first_row, int nrows);
 
 /* ---- tables ------------------------------------------------------------------------------ */
