@@ -275,6 +275,7 @@ extern "C" int fib_host_free(void* p) {
   return 0;
 }
 
+static int create_resources(fib_ctx* c);
 extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   if (!cfg || !out) return fail(FIB_E_ARG, "cfg/out is NULL");
   if (cfg->struct_size != sizeof(fib_config))
@@ -315,6 +316,20 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   c->g.row0 = row0;
   c->g.rows = rows;
   c->g.pitch = (cfg->width + 31) / 32 * 32;
+  // a failure half way (e.g. out of memory at 32768^2 on a busy GPU) must release what exists
+  const int rc = create_resources(c);
+  if (rc) {
+    const std::string why = g_err;
+    fib_destroy(c);
+    g_err = why;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+static int create_resources(fib_ctx* c) {
+  const fib_config* cfg = &c->cfg;
   switch (cfg->model) {
     case FIB_FENTON4V: c->nvars = 4; c->dt_per_step = 10; c->names = kFentonVars; break;
     case FIB_BR: c->nvars = 8; c->dt_per_step = 5; c->names = kBrVars; break;
@@ -362,20 +377,20 @@ extern "C" int fib_create(const fib_config* cfg, fib_ctx** out) {
   }
   memset(c->cheb, 0, sizeof c->cheb);
   CU(cudaStreamSynchronize(c->stream));
-  *out = c;
   return 0;
 }
 
 extern "C" int fib_destroy(fib_ctx* c) {
   if (!c) return 0;
   DevGuard dg(c->cfg.device);
-  cudaStreamSynchronize(c->stream);
-  cudaStreamSynchronize(c->comm_stream);
-  cudaStreamSynchronize(c->copy_stream);
+  // every handle may still be null: fib_create destroys a partially built context on failure
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   cudaFree(c->snap);
-  cudaEventDestroy(c->ev_snap_ready);
-  cudaEventDestroy(c->ev_snap_done);
-  cudaStreamDestroy(c->copy_stream);
+  if (c->ev_snap_ready) cudaEventDestroy(c->ev_snap_ready);
+  if (c->ev_snap_done) cudaEventDestroy(c->ev_snap_done);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
   for (int b = 0; b < 2; ++b) cudaFree(c->x[b]);
@@ -390,13 +405,11 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->lut_t);
   cudaFree(c->red);
   for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
-  cudaEventDestroy(c->ev_start);
-  cudaEventDestroy(c->ev_stop);
-  cudaEventDestroy(c->ev_bnd);
-  cudaEventDestroy(c->ev_comm);
-  cudaEventDestroy(c->ev_group);
-  cudaStreamDestroy(c->stream);
-  cudaStreamDestroy(c->comm_stream);
+  for (cudaEvent_t e : {c->ev_start, c->ev_stop, c->ev_bnd, c->ev_comm, c->ev_group})
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  cudaGetLastError();      // a failed creation may have left a sticky-free error behind
   delete c;
   return 0;
 }
