@@ -148,6 +148,11 @@ class ClockSampler:
 
     def stop(self):
         if self.proc:
+            # a run shorter than nvidia-smi's start-up (reduced --size) would end without any
+            # sample: wait for the first one rather than report nothing
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0 and self.proc.poll() is None:
+                time.sleep(0.05)
             self.proc.terminate()
         sm = sorted(float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit())
         reasons = set()

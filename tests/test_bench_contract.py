@@ -38,3 +38,33 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_is_rank0_only_under_a_multi_rank_launch():
     lines = run({'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}, '--gpus', '2', '--steps', '1', '--warmup', '1')
     assert lines == []
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_one_contract_line(cuda_device):
+    """`python bench.py` at a reduced grid (4096^2, still >> L2): one JSON line with every key of
+    the contract, the device-timed value consistent with ms_per_step, a non-trivial e2e leg and
+    kernels of this library launched inside the timed region."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--size', '4096', '--steps', '3',
+                        '--warmup', '3', '--no-cpu'], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    # (--no-cpu skips the 20-second cpu_baseline leg; the CPU test above covers that object)
+    need = [k for k in NEED if k not in ('impl', 'cpu_baseline')] + ['gpu_launches', 'clocks', 'roofline']
+    assert [k for k in need if k not in d] == []
+    cells = 4096.0 * 4096.0
+    assert abs(d['value'] - cells * 10 / (d['ms_per_step'] * 1e-3) / 1e9) <= 1e-6 * d['value']
+    assert d['steps'] == 3 and d['warmup'] == 3 and d['n_gpus'] == 1
+    spl = d['config']['time_steps_per_launch']
+    assert d['gpu_launches'] == 3 * 10 // spl
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert abs(r['achieved'] - 32.0 * d['value']) <= 1e-6 * r['achieved']      # 32 B per cell-step
+    e = d['e2e']
+    assert 0 < e['value'] < d['value'] and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0
+    assert d['clocks']['sm_mhz'] > 0
