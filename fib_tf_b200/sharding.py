@@ -26,13 +26,20 @@ def owner_of_row(height, nranks, row):
     raise IndexError(row)
 
 
-def halo_plan(height, nranks, rank):
-    """What rank exchanges after every time step: list of (peer, send_row, recv_halo) in GLOBAL
-    rows; global rows 0 and H-1 are physical borders, shard seams are ordinary interior."""
+def halo_plan(height, nranks, rank, depth=1):
+    """What rank exchanges after every launch: list of (peer, send_row, recv_halo) in GLOBAL rows;
+    global rows 0 and H-1 are physical borders, shard seams are ordinary interior.
+
+    depth = time steps per launch = rows per message: 1 -> one row of the diffusing variable per
+    step; 2 -> with two time steps per launch (csrc/fib_fused.cuh) `send_row` and `recv_halo` are
+    the FIRST of `depth` consecutive rows, of every state plane (the first step is recomputed on
+    the neighbour's edge rows, which needs all of its variables)."""
     row0, rows = partition_rows(height, nranks)[rank]
+    if depth < 1 or (nranks > 1 and rows < depth):
+        raise ValueError('a shard of %d rows cannot exchange %d-row halos' % (rows, depth))
     plan = []
     if rank > 0:
-        plan.append((rank - 1, row0, row0 - 1))
+        plan.append((rank - 1, row0, row0 - depth))
     if rank + 1 < nranks:
-        plan.append((rank + 1, row0 + rows - 1, row0 + rows))
+        plan.append((rank + 1, row0 + rows - depth, row0 + rows))
     return plan

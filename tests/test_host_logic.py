@@ -114,3 +114,21 @@ def test_headless_screen_keeps_the_reference_protocol(tmp_path):
         im.imshow(np.zeros([3, 3]))
     saved = im.save(str(tmp_path / 'frame.npy'))
     assert np.array_equal(np.load(saved), im.last)
+
+
+def test_halo_plan_two_rows_deep_for_two_steps_per_launch():
+    """depth = 2: each message is two consecutive rows; what a rank sends is what its neighbour
+    expects, and the received rows are exactly the two rows beyond the shard."""
+    H, n = 37, 4
+    parts = partition_rows(H, n)
+    plans = [halo_plan(H, n, r, depth=2) for r in range(n)]
+    for r, plan in enumerate(plans):
+        row0, rows = parts[r]
+        for peer, send, recv in plan:
+            assert row0 <= send and send + 2 <= row0 + rows              # I own what I send
+            back = [p for p in plans[peer] if p[0] == r]
+            assert len(back) == 1 and back[0][2] == send                  # the peer receives exactly that
+            assert recv in (row0 - 2, row0 + rows)                        # just outside my block
+    assert len(plans[0]) == 1 and len(plans[-1]) == 1 and all(len(p) == 2 for p in plans[1:-1])
+    with pytest.raises(ValueError):
+        halo_plan(5, 4, 3, depth=2)                                       # a 1-row shard cannot
