@@ -20,7 +20,7 @@
 #define FIB_BR_VEC_SLOW 2
 #endif
 #ifndef FIB_BR_MINB_SLOW
-#define FIB_BR_MINB_SLOW 6
+#define FIB_BR_MINB_SLOW 7
 #endif
 #ifndef FIB_BR_MINB_SLOW_EXACT
 #define FIB_BR_MINB_SLOW_EXACT 7
