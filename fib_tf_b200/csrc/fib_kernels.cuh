@@ -22,7 +22,7 @@ namespace fib {
 //   NEED_RAW      reaction term reads the un-enforced centre value (Fenton 4v, fenton.py:101)
 //   NEED_LAP      step needs the stencil (false for the Courtemanche 'slow' op)
 //   STORE_X       step writes the diffusing variable
-//   MIN_BLOCKS    resident CTAs per SM the register allocator must leave room for
+//   min_blocks(v) resident CTAs per SM the register allocator must leave room for, v cells per thread
 //   PREFETCH      prefetch the next marching row's lines into L1
 //   stores(k)     plane k is written by this step
 //   struct Params (uniform scalars / small tables; lives in the kernel parameter bank)
@@ -61,7 +61,7 @@ inline bool& pdl_enabled() {
 }
 
 template <class M, int VEC, int R, int BY, bool PHASE>
-__global__ void __launch_bounds__(kBX* BY, M::MIN_BLOCKS)
+__global__ void __launch_bounds__(kBX* BY, M::min_blocks(VEC))
 step_kernel(const Geom g, const StepArgs<M> a) {
   // Programmatic dependent launch: let the NEXT time step's kernel be scheduled while this one
   // drains (its CTAs park at their own griddepcontrol.wait), and do not touch memory before the

@@ -183,6 +183,10 @@ struct BeelerReuter {
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
       SLOW ? (CHEBY ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
+  // the one-cell-per-thread flavour of small grids keeps 6 (512^2 + hole: 45.7 vs 44.2 at 7)
+  static __host__ __device__ constexpr int min_blocks(int vec) {
+    return (SLOW && CHEBY && vec == 1) ? 6 : MIN_BLOCKS;
+  }
   static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
   static constexpr bool NEED_LAP = true;

@@ -267,6 +267,7 @@ struct Courtemanche {
   static constexpr int AUTO_R = LUT ? 2 : 1;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
       MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
+  static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
   static constexpr bool PREFETCH = false;
   static constexpr bool NEED_RAW = false; // V = enforce_boundary(V0) everywhere (court.py:126-127)
   static constexpr bool NEED_LAP = MODE != COURT_SLOW;
