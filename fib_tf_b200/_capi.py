@@ -16,9 +16,11 @@ LIB_PATH = os.environ.get('FIB_B200_LIB') or os.path.join(_HERE, 'libfibb200.so'
 FENTON4V, BR, COURT, COURT_ULTRA = 0, 1, 2, 3
 F_CHEBY, F_SKIP, F_LUT, F_ULTRA_SLOW, F_NO_CHRONIC, F_NO_GRAPH = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 F_NO_CLIP = 0x40
+F_CHEBY_STRICT, F_NO_PERSIST = 0x80, 0x100
+PROBE_RING = 4096
 OP_ODE, OP_SLOW = 0, 1
 TABLE_BR_CHEBY, TABLE_COURT_LUT = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 INTER_COLS = 32
 
 # courtemanche.h:105-134 column order (+ the two court_ultra.py:445-450 extras)
@@ -62,6 +64,15 @@ _SIGNATURES = {
     'fib_snapshot_begin': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_snapshot_wait': (C.c_int, [_P]),
     'fib_set_rect': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'fib_set_rect_async': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'fib_last_kernel': (C.c_int, [C.c_char_p, C.c_size_t]),
+    'fib_probe_watch': (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    'fib_probe_fetch': (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    'fib_count_below': (C.c_int, [_P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    'fib_op_enforce_boundary': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P]),
+    'fib_op_laplace': (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    'fib_op_rush_larsen': (C.c_int, [C.c_int, _P, _P, _P, C.c_size_t, C.c_float, C.c_int, _P]),
     'fib_set_phase': (C.c_int, [_P, _P, C.c_int, C.c_int]),
     'fib_set_table': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     'fib_get_table': (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
@@ -189,6 +200,10 @@ class Context:
     def get_state(self, var, out=None):
         if out is None:
             out = np.empty((self.rows, self.width), dtype=np.float32)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags['C_CONTIGUOUS']
+              or not out.flags['WRITEABLE'] or out.shape != (self.rows, self.width)):
+            raise FibError('get_state: `out` must be a writeable C-contiguous float32 array of shape %r'
+                           % ((self.rows, self.width),))
         check(lib().fib_get_state(self._h, self.var(var), out.ctypes.data_as(_P), out.size))
         return out
 
@@ -197,6 +212,9 @@ class Context:
         steps enqueued afterwards.  snapshot_wait() completes it."""
         if pinned_out.dtype != np.float32 or not pinned_out.flags['C_CONTIGUOUS']:
             raise FibError('snapshot target must be a C-contiguous float32 array')
+        if pinned_out.shape != (self.rows, self.width):
+            raise FibError('snapshot target must have the shard shape %r' % ((self.rows, self.width),))
+        # (that the memory is page-locked is checked by the library: cudaPointerGetAttributes)
         check(lib().fib_snapshot_begin(self._h, self.var(var), pinned_out.ctypes.data_as(_P),
                                        pinned_out.size))
 
@@ -211,6 +229,15 @@ class Context:
     def set_rect(self, var, r0, c0, block):
         a, p = _f32c(block)
         check(lib().fib_set_rect(self._h, self.var(var), r0, r0 + a.shape[0], c0, c0 + a.shape[1], p))
+
+    def set_rect_async(self, var, r0, c0, pinned_block):
+        """Enqueue-only upload of a block that lives in page-locked memory (pinned_empty); the block
+        must stay unchanged until the next sync()."""
+        a = pinned_block
+        if a.dtype != np.float32 or not a.flags['C_CONTIGUOUS'] or a.ndim != 2:
+            raise FibError('set_rect_async: the block must be a 2-D C-contiguous float32 array')
+        check(lib().fib_set_rect_async(self._h, self.var(var), r0, r0 + a.shape[0], c0, c0 + a.shape[1],
+                                       a.ctypes.data_as(_P)))
 
     def set_phase(self, phase_rows, first_row=0):
         if phase_rows is None:
@@ -248,6 +275,21 @@ class Context:
         v = C.c_float()
         check(lib().fib_probe(self._h, self.var(var), row, col, C.byref(v)))
         return np.float32(v.value)
+
+    def probe_watch(self, var, row, col):
+        """Record cell (row, col) of `var` into the device ring after every iteration (row < 0: stop)."""
+        check(lib().fib_probe_watch(self._h, self.var(var) if row >= 0 else 0, row, col))
+
+    def probe_fetch(self, max_values=PROBE_RING):
+        out = np.empty(max_values, dtype=np.float32)
+        n = C.c_size_t()
+        check(lib().fib_probe_fetch(self._h, out.ctypes.data_as(_P), max_values, C.byref(n)))
+        return out[:n.value]
+
+    def count_below(self, var, sub, div, cutoff, w_min):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib().fib_count_below(self._h, self.var(var), sub, div, cutoff, w_min, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def weighted_sum(self, var):
         a, b = C.c_double(), C.c_double()
@@ -306,6 +348,56 @@ def comm_unique_id():
 def step_group(contexts, op=OP_ODE, n_iter=1):
     arr = (_P * len(contexts))(*[c._h for c in contexts])
     check(lib().fib_step_group(arr, len(contexts), op, n_iter))
+
+
+def last_kernel():
+    """Name of the step-kernel flavour launched last by this thread (fib_last_kernel)."""
+    buf = C.create_string_buffer(160)
+    check(lib().fib_last_kernel(buf, 160))
+    return buf.value.decode()
+
+
+def _plane(a, name):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2:
+        raise FibError('%s: expected a 2-D plane, got shape %r' % (name, a.shape))
+    return a
+
+
+def op_enforce_boundary(x, device=0):
+    """IonicModel.enforce_boundary (ionic.py:107-113) on a dense [h, w] plane, on the device."""
+    a = _plane(x, 'enforce_boundary')
+    out = np.empty_like(a)
+    check(lib().fib_op_enforce_boundary(device, a.ctypes.data_as(_P), a.shape[0], a.shape[1],
+                                        out.ctypes.data_as(_P)))
+    return out
+
+
+def op_laplace(x, phase=None, mode=0, device=0):
+    """IonicModel.laplace (ionic.py:44-60): mode 0 = REFLECT pad + 9-point stencil (+ phase term);
+    mode 1 = the step kernels' collapsed index map on a raw plane = laplace(enforce_boundary(x));
+    mode 2 = the phase-field term alone (ionic.py:70-81)."""
+    a = _plane(x, 'laplace')
+    ph = None
+    if phase is not None:
+        ph = _plane(phase, 'phase')
+        if ph.shape != a.shape:
+            raise FibError('laplace: phase shape %r != plane shape %r' % (ph.shape, a.shape))
+    out = np.empty_like(a)
+    check(lib().fib_op_laplace(device, a.ctypes.data_as(_P), ph.ctypes.data_as(_P) if ph is not None else None,
+                               a.shape[0], a.shape[1], mode, out.ctypes.data_as(_P)))
+    return out
+
+
+def op_rush_larsen(g, g_inf, tau, dt, strict=False, device=0):
+    """IonicModel.rush_larsen (ionic.py:115-123), elementwise on arrays of one shape."""
+    g = np.ascontiguousarray(g, dtype=np.float32)
+    gi = np.ascontiguousarray(np.broadcast_to(np.asarray(g_inf, np.float32), g.shape))
+    t = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, np.float32), g.shape))
+    out = np.empty_like(g)
+    check(lib().fib_op_rush_larsen(device, g.ctypes.data_as(_P), gi.ctypes.data_as(_P), t.ctypes.data_as(_P),
+                                   g.size, float(dt), 1 if strict else 0, out.ctypes.data_as(_P)))
+    return out
 
 
 def device_count():

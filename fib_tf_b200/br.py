@@ -6,6 +6,7 @@ fib_tf_b200.br -- drop-in for the reference's br.py: the modified 8-variable Bee
          (br.py:207-252, 289-331); the 12x9 coefficient table is computed HERE on the host in
          fp64 exactly like the reference and handed to the kernel (FIB_TABLE_BR_CHEBY);
   skip   multi-rate: the slow gates xi, j, d, f advance once per 5 steps with 5*dt (br.py:96-107).
+  cheby_strict (extra, optional)  the polynomial gates in the reference's exact operation order.
 
 One run() iteration = 5 time steps = 5 launches of the fused kernel (one CUDA graph).
 """
@@ -45,6 +46,11 @@ class BeelerReuter(IonicModel):
         """Initial state br.py:71-82; S1 = column 1 of V set to 10 mV."""
         super().define()
         flags = (_capi.F_CHEBY if self.cheby else 0) | (_capi.F_SKIP if self.skip else 0)
+        # config['cheby_strict'] (optional, default False): evaluate the polynomial gates in the
+        # reference's own fp32 operation order (br.py:215,289-301,327-331) instead of Horner's scheme;
+        # slower, used to show how closely the reference's result is defined (DESIGN.md section 4)
+        if self.cheby and self.__dict__.get('cheby_strict'):
+            flags |= _capi.F_CHEBY_STRICT
         ctx = self._make_context(flags)
         init = {'V': -84.624, 'C': 1e-4, 'M': 0.01, 'H': 0.988, 'J': 0.975, 'D': 0.003,
                 'F': 0.994, 'XI': 0.0001}

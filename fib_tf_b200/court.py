@@ -7,7 +7,7 @@ Multi-rate by driver convention, exactly like the reference (court.py:94-103, 61
   * fire_op('slow') advances the other 17 states with 10*dt, evaluated on the CURRENT state
     (drivers fire it every 10th iteration)                        -> kernel mode COURT_SLOW
 With config['lut']=True the 30 voltage-only intermediates come from the 150x30 table of
-courtemanche.h (truncating lookup), staged in shared memory.
+courtemanche.h (truncating lookup), read from a transposed copy [30][160] that stays L1-resident (see csrc/model_court.cuh for the shared-memory A/B).
 """
 import numpy as np
 

@@ -87,9 +87,9 @@ def run_small(config, im, cyclelengths, radius=50, i0=0):
         if i == s2:
             m.fire_op('s2')
         if i % 5000 == 0:
-            image, phase = m.image(), m.phase
-            rho = np.sum(image[phase > 1e-3] < 0.2) / np.sum(phase > 1e-3)     # cutoff -55 mV
-            print('rho = %.4f' % rho)
+            # rho = np.sum(image[phase > 1e-3] < 0.2) / np.sum(phase > 1e-3), cutoff -55 mV
+            # (court_ultra.py:504-509), as a threshold count on the device
+            print('rho = %.4f' % m.excitable_fraction(0.2, 1e-3))
     np.save('state_small', m.state)
     return m.state
 

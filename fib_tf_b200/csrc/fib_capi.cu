@@ -130,6 +130,11 @@ struct fib_ctx {
   uint64_t launches = 0;
   std::vector<GraphKey> graphs;
   double* red = nullptr;              // 2 doubles for reductions
+  // device-side cycle-length probe (fib_probe_watch): one watched cell, a ring of recorded values
+  float* ring = nullptr;
+  unsigned long long* ring_count = nullptr;
+  unsigned long long ring_fetched = 0;
+  int watch_var = -1, watch_row = -1, watch_col = -1;
   float* weights[4] = {nullptr, nullptr, nullptr, nullptr};   // user masks, halo layout like phase
   // NCCL
   void* comm = nullptr;
@@ -231,6 +236,81 @@ __global__ void nonfinite_kernel(const float* __restrict__ x, Geom g, int xhalo,
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
 }
 
+// fib_probe_watch: append the watched cell to the ring (one thread; a node of the iteration graph)
+__global__ void probe_record_kernel(const float* __restrict__ src, float* __restrict__ ring,
+                                    unsigned long long* __restrict__ count) {
+  const unsigned long long n = *count;
+  ring[n % FIB_PROBE_RING] = *src;
+  *count = n + 1;
+}
+
+// a host-side write (stimulus, assign) after the iteration: the reference evaluates its probe AFTER
+// the driver's loop body (ionic.py:202-216), so the last recorded value follows the write
+__global__ void probe_update_kernel(const float* __restrict__ src, float* __restrict__ ring,
+                                    const unsigned long long* __restrict__ count) {
+  const unsigned long long n = *count;
+  if (n) ring[(n - 1) % FIB_PROBE_RING] = *src;
+}
+
+// court_ultra.py:504-509: cells with weight > w_min, and among them those whose normalised value
+// (x - sub) / div (the image() of br.py:337-343 / court.py:574-580, same fp32 operations) < cutoff
+__global__ void count_below_kernel(const float* __restrict__ x, const float* __restrict__ w, Geom g,
+                                   int xhalo, float sub, float div, float cutoff, float w_min,
+                                   unsigned long long* out) {
+  unsigned long long below = 0, total = 0;
+  for (int lr = blockIdx.x; lr < g.rows; lr += gridDim.x)
+    for (int c = threadIdx.x; c < g.W; c += blockDim.x) {
+      const float wv = w ? w[(size_t)(lr + 1) * g.pitch + c] : 1.0f;
+      if (wv > w_min) {
+        ++total;
+        const float img = __fdiv_rn(__fsub_rn(x[(size_t)(lr + xhalo) * g.pitch + c], sub), div);
+        below += img < cutoff;
+      }
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    below += __shfl_down_sync(0xffffffffu, below, o);
+    total += __shfl_down_sync(0xffffffffu, total, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, below); atomicAdd(out + 1, total); }
+}
+
+// ---- op-level entry points (fib_op_*): IonicModel's helpers on dense planes ----------------------
+__global__ void op_enforce_kernel(const float* __restrict__ x, int h, int w, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= w) return;
+  out[(size_t)r * w + c] = x[(size_t)clampi(r, 1, h - 2) * w + clampi(c, 1, w - 2)];   // ionic.py:107-113
+}
+// mode 0: Xp = REFLECT pad of x (ionic.py:49-50); mode 1: the step kernels' collapsed map on a raw
+// plane, Xp[r][c] = x[clamp(r,1,h-2)][clamp(c,1,w-2)] (fib_stencil.cuh); mode 2: phase term only
+__global__ void op_laplace_kernel(const float* __restrict__ x, const float* __restrict__ ph, int h, int w,
+                                  int mode, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= w) return;
+  auto X = [&](int rr, int cc) {
+    const int r2 = mode == 1 ? clampi(rr, 1, h - 2) : reflecti(rr, h);
+    const int c2 = mode == 1 ? clampi(cc, 1, w - 2) : reflecti(cc, w);
+    return x[(size_t)r2 * w + c2];
+  };
+  auto P = [&](int rr, int cc) { return ph[(size_t)reflecti(rr, h) * w + reflecti(cc, w)]; };
+  float lap = 0.f;
+  if (mode != 2)
+    lap = lap9(X(r - 1, c), X(r + 1, c), X(r, c - 1), X(r, c + 1), X(r - 1, c - 1), X(r + 1, c - 1),
+               X(r - 1, c + 1), X(r + 1, c + 1), X(r, c));
+  if (ph) {
+    const float t = phase_term(X(r - 1, c), X(r + 1, c), X(r, c - 1), X(r, c + 1), P(r - 1, c), P(r + 1, c),
+                               P(r, c - 1), P(r, c + 1), P(r, c));
+    lap = mode == 2 ? t : __fadd_rn(lap, t);
+  }
+  out[(size_t)r * w + c] = lap;
+}
+__global__ void op_rush_larsen_kernel(const float* __restrict__ g, const float* __restrict__ gi,
+                                      const float* __restrict__ tau, size_t n, float neg_dt, int strict,
+                                      float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = strict ? rush_larsen_strict(g[i], gi[i], tau[i], neg_dt) : rush_larsen(g[i], gi[i], tau[i], neg_dt);
+}
+
 __global__ void court_inter_kernel(const float* __restrict__ v, int n, float* __restrict__ out,
                                    int ncols) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,6 +339,11 @@ __global__ void court_lut_kernel(float* __restrict__ lut) {   // courtemanche.h:
 // ------------------------------------------------------------------------------------------
 extern "C" int fib_version(void) { return FIB_ABI_VERSION; }
 extern "C" const char* fib_last_error(void) { return g_err.c_str(); }
+extern "C" int fib_last_kernel(char* buf, size_t n) {
+  if (!buf || n == 0) return fail(FIB_E_ARG, "buf is NULL");
+  snprintf(buf, n, "%s", last_kernel_name());
+  return 0;
+}
 extern "C" int fib_device_count(int* count) {
   if (!count) return fail(FIB_E_ARG, "count is NULL");
   CU(cudaGetDeviceCount(count));
@@ -404,6 +489,8 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->lut);
   cudaFree(c->lut_t);
   cudaFree(c->red);
+  cudaFree(c->ring);
+  cudaFree(c->ring_count);
   for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
   for (cudaEvent_t e : {c->ev_start, c->ev_stop, c->ev_bnd, c->ev_comm, c->ev_group})
     if (e) cudaEventDestroy(e);
@@ -438,9 +525,26 @@ static float* owned_rows(fib_ctx* c, int var) {
   const PlaneRef p = plane_of(c, var);
   return p.base + (size_t)p.halo * c->g.pitch;
 }
-// a host write into `var` invalidates the neighbours' copies of the rows they hold as halo
+__global__ void probe_update_kernel(const float* __restrict__ src, float* __restrict__ ring,
+                                    const unsigned long long* __restrict__ count);
+static PlaneRef plane_of(fib_ctx* c, int var);
+// a host write into `var` invalidates the neighbours' copies of the rows they hold as halo, and
+// the last value the cycle-length probe recorded if it watches this plane (enqueue-only)
 static void mark_written(fib_ctx* c, int var) {
   if (var == 0 || c->fuse == 2) c->halo_dirty = true;
+  if (var == c->watch_var) {
+    const PlaneRef p = plane_of(c, var);
+    const float* src = p.base + (size_t)(p.halo + c->watch_row - c->g.row0) * c->g.pitch + c->watch_col;
+    probe_update_kernel<<<1, 1, 0, c->stream>>>(src, c->ring, c->ring_count);
+    c->launches++;
+  }
+}
+// a halo exchange still running on the side stream must land before anything else touches the
+// diffusing variable's buffers on the main stream
+static cudaError_t wait_comm(fib_ctx* c) {
+  if (!c->comm_pending) return cudaSuccess;
+  c->comm_pending = false;
+  return cudaStreamWaitEvent(c->stream, c->ev_comm, 0);
 }
 
 extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
@@ -449,6 +553,7 @@ extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
   if (n != (size_t)c->g.rows * c->g.W)
     return fail(FIB_E_ARG, "fib_set_state: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
   DevGuard dg(c->cfg.device);
+  CU(wait_comm(c));
   CU(cudaMemcpy2DAsync(owned_rows(c, var), c->g.pitch * sizeof(float), host, c->g.W * sizeof(float),
                        c->g.W * sizeof(float), c->g.rows, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -487,6 +592,13 @@ extern "C" int fib_snapshot_begin(fib_ctx* c, int var, float* host_pinned, size_
   if (n != (size_t)c->g.rows * c->g.W)
     return fail(FIB_E_ARG, "fib_snapshot_begin: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
   DevGuard dg(c->cfg.device);
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, host_pinned) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      return fail(FIB_E_ARG, "fib_snapshot_begin needs page-locked host memory (fib_host_alloc)");
+    }
+  }
   if (!c->snap) CU(cudaMalloc(&c->snap, c->plane_floats() * sizeof(float)));
   if (c->snap_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_snap_done, 0));   // staging still in use
   CU(cudaMemcpyAsync(c->snap, owned_rows(c, var), c->plane_floats() * sizeof(float),
@@ -509,18 +621,32 @@ extern "C" int fib_snapshot_wait(fib_ctx* c) {
   return 0;
 }
 
-extern "C" int fib_set_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host) {
+static int set_rect_impl(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host, bool sync) {
   if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
     return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
   DevGuard dg(c->cfg.device);
+  if (!sync) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      return fail(FIB_E_ARG, "fib_set_rect_async needs page-locked host memory (fib_host_alloc)");
+    }
+  }
+  CU(wait_comm(c));
   float* dst = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch + c0;
   CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)(c1 - c0) * sizeof(float),
                        (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (sync) CU(cudaStreamSynchronize(c->stream));
   mark_written(c, var);
   return 0;
+}
+extern "C" int fib_set_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host) {
+  return set_rect_impl(c, var, r0, r1, c0, c1, host, true);
+}
+extern "C" int fib_set_rect_async(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host) {
+  return set_rect_impl(c, var, r0, r1, c0, c1, host, false);
 }
 
 extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
@@ -744,6 +870,7 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
       // br.py:96-107: skip -> solve(n=5) then 4x solve(n=0); else 5x solve(n=1)
       const int n = (fl & FIB_F_SKIP) ? (sub == 0 ? 5 : 0) : 1;
       const bool cheby = fl & FIB_F_CHEBY;
+      const bool strict = cheby && (fl & FIB_F_CHEBY_STRICT);
       if (cheby && !c->have_cheb)
         return fail(FIB_E_STATE, "cheby=True but FIB_TABLE_BR_CHEBY has not been set");
       auto go = [&](auto tag) {
@@ -754,13 +881,16 @@ static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows) {
         a.p.neg_dt = (float)(-dt);
         a.p.neg_dt_slow = (float)(-(dt * n));
         a.p.ddt = (float)(c->cfg.diff * dt);
-        // S_i = 2^(i-1) x^i (br.py:289-301): hand the kernel plain monomial coefficients
+        // S_i = 2^(i-1) x^i (br.py:289-301): hand the kernel plain monomial coefficients (the strict
+        // flavour evaluates the S-basis sum itself and takes the table as it is)
         for (int g = 0; g < 12; ++g)
-          for (int i = 0; i < 9; ++i) a.p.poly[g][i] = i < 2 ? c->cheb[g][i] : ldexpf(c->cheb[g][i], i - 1);
+          for (int i = 0; i < 9; ++i)
+            a.p.poly[g][i] = (i < 2 || strict) ? c->cheb[g][i] : ldexpf(c->cheb[g][i], i - 1);
         return launch_step<M>(c->g, a, c->stream, c->sms);
       };
-      if (cheby) e = n > 0 ? go(BeelerReuter<true, true>()) : go(BeelerReuter<true, false>());
-      else       e = n > 0 ? go(BeelerReuter<false, true>()) : go(BeelerReuter<false, false>());
+      if (strict)     e = n > 0 ? go(BeelerReuter<2, true>()) : go(BeelerReuter<2, false>());
+      else if (cheby) e = n > 0 ? go(BeelerReuter<1, true>()) : go(BeelerReuter<1, false>());
+      else            e = n > 0 ? go(BeelerReuter<0, true>()) : go(BeelerReuter<0, false>());
       break;
     }
     case FIB_COURT: {
@@ -825,6 +955,16 @@ static int nccl_exchange(fib_ctx* c, int b, cudaStream_t st) {
   return 0;
 }
 
+// fib_probe_watch: after an ODE iteration, append the watched cell of the CURRENT buffers to the ring
+static int record_probe(fib_ctx* c, int op) {
+  if (c->watch_var < 0 || op != FIB_OP_ODE) return 0;
+  const float* src = owned_rows(c, c->watch_var) + (size_t)(c->watch_row - c->g.row0) * c->g.pitch + c->watch_col;
+  probe_record_kernel<<<1, 1, 0, c->stream>>>(src, c->ring, c->ring_count);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
 static int run_iteration_plain(fib_ctx* c, int op) {
   const int ns = substeps_of(c, op);
   for (int s = 0; s < ns; s += c->fuse) {
@@ -832,7 +972,7 @@ static int run_iteration_plain(fib_ctx* c, int op) {
     if (r) return r;
     if (op_writes_x(c, op)) c->cur ^= 1;
   }
-  return 0;
+  return record_probe(c, op);
 }
 
 // boundary rows first, halo exchange on the side stream overlapped with the interior rows
@@ -866,11 +1006,15 @@ static int run_iteration_nccl(fib_ctx* c, int op) {
     }
     c->cur ^= 1;
   }
-  return 0;
+  return record_probe(c, op);
 }
 
+// Every rank must take part in an exchange, but a host write (fib_set_state / fib_set_rect /
+// fib_stimulate) is local knowledge: a rank cannot know whether its neighbour's edge rows changed.
+// So fib_step ALWAYS refreshes the halos of the current buffer first (one small grouped send/recv
+// per fib_step call, idempotent when nothing was written): the decision is the same on all ranks.
 static int refresh_halos_nccl(fib_ctx* c) {
-  if (!c->halo_dirty) return 0;
+  CU(wait_comm(c));
   int r = nccl_exchange(c, c->cur, c->stream);
   if (r) return r;
   c->halo_dirty = false;
@@ -922,8 +1066,8 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
       c->graphs.push_back({op, cur0, exec});
     }
     CU(cudaGraphLaunch(exec, c->stream));
-    const int nl = substeps_of(c, op) / c->fuse;      // launches per iteration
-    c->launches += nl;
+    const int nl = substeps_of(c, op) / c->fuse;      // step launches per iteration
+    c->launches += nl + ((c->watch_var >= 0 && op == FIB_OP_ODE) ? 1 : 0);
     if (op_writes_x(c, op) && (nl & 1)) c->cur ^= 1;
   }
   return 0;
@@ -1011,7 +1155,7 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
     if ((r = group_wait_neighbours(cs, n))) return r;
     for (int i = 0; i < n; ++i) cs[i]->halo_dirty = false;
   }
-  for (int it = 0; it < n_iter; ++it)
+  for (int it = 0; it < n_iter; ++it) {
     for (int s = 0; s < ns; s += cs[0]->fuse) {
       for (int i = 0; i < n; ++i) {
         DevGuard dg(cs[i]->cfg.device);
@@ -1023,6 +1167,11 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
         for (int i = 0; i < n; ++i) cs[i]->cur ^= 1;
       }
     }
+    for (int i = 0; i < n; ++i) {
+      DevGuard dg(cs[i]->cfg.device);
+      if ((r = record_probe(cs[i], op))) return r;
+    }
+  }
   return 0;
 }
 
@@ -1034,10 +1183,7 @@ extern "C" int fib_stimulate(fib_ctx* c, int var, int r0, int r1, int c0, int c1
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
-  if (c->comm_pending) {
-    CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
-    c->comm_pending = false;
-  }
+  CU(wait_comm(c));
   dim3 block(128), grid((c->g.W + 127) / 128, min(c->g.rows, 65535));
   const PlaneRef pl = plane_of(c, var);
   stim_kernel<<<grid, block, 0, c->stream>>>(pl.base, c->g, pl.halo, r0, r1, c0, c1, value, floor_v);
@@ -1121,6 +1267,156 @@ extern "C" int fib_masked_sum(fib_ctx* c, int var, int slot, double* sum_wx, dou
   if (slot < 0 || slot >= 4 || !c->weights[slot]) return fail(FIB_E_STATE, "weight slot %d is empty", slot);
   DevGuard dg(c->cfg.device);
   return reduce_weighted(c, var, c->weights[slot], sum_wx, sum_w);
+}
+
+static void drop_graphs(fib_ctx* c) {
+  for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);
+  c->graphs.clear();
+}
+
+extern "C" int fib_probe_watch(fib_ctx* c, int var, int row, int col) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  CU(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);                       // the record node is part of the iteration graph
+  if (row < 0) {
+    c->watch_var = -1;
+    return 0;
+  }
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  if (row < c->g.row0 || row >= c->g.row0 + c->g.rows || col < 0 || col >= c->g.W)
+    return fail(FIB_E_ARG, "probe (%d,%d) is not in this shard", row, col);
+  if (!c->ring) {
+    CU(cudaMalloc(&c->ring, FIB_PROBE_RING * sizeof(float)));
+    CU(cudaMalloc(&c->ring_count, sizeof(unsigned long long)));
+  }
+  CU(cudaMemsetAsync(c->ring_count, 0, sizeof(unsigned long long), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->ring_fetched = 0;
+  c->watch_var = var;
+  c->watch_row = row;
+  c->watch_col = col;
+  return 0;
+}
+
+extern "C" int fib_probe_fetch(fib_ctx* c, float* out, size_t max, size_t* n) {
+  if (!c || !n || (!out && max)) return fail(FIB_E_ARG, "NULL argument");
+  *n = 0;
+  if (c->watch_var < 0) return fail(FIB_E_STATE, "no probe is being watched (fib_probe_watch)");
+  DevGuard dg(c->cfg.device);
+  unsigned long long count = 0;
+  CU(cudaMemcpyAsync(&count, c->ring_count, sizeof count, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  unsigned long long first = c->ring_fetched;
+  if (count - first > FIB_PROBE_RING) first = count - FIB_PROBE_RING;      // the oldest were overwritten
+  unsigned long long take = count - first;
+  if (take > max) take = max;
+  // at most two contiguous pieces of the ring
+  unsigned long long done = 0;
+  while (done < take) {
+    const unsigned long long pos = (first + done) % FIB_PROBE_RING;
+    unsigned long long len = FIB_PROBE_RING - pos;
+    if (len > take - done) len = take - done;
+    CU(cudaMemcpyAsync(out + done, c->ring + pos, len * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    done += len;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->ring_fetched = first + take;
+  *n = (size_t)take;
+  return 0;
+}
+
+extern "C" int fib_count_below(fib_ctx* c, int var, float sub, float div, float cutoff, float w_min,
+                               uint64_t* below, uint64_t* total) {
+  if (!c || !below || !total) return fail(FIB_E_ARG, "NULL argument");
+  if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
+  DevGuard dg(c->cfg.device);
+  CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
+  const PlaneRef pl = plane_of(c, var);
+  count_below_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(
+      pl.base, c->phase, c->g, pl.halo, sub, div, cutoff, w_min, reinterpret_cast<unsigned long long*>(c->red));
+  CU(cudaGetLastError());
+  c->launches++;
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, c->red, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *below = h[0];
+  *total = h[1];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// op-level entry points (eager, dense host planes)
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+  float* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+};
+static int op_device(int device) {
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(FIB_E_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  return 0;
+}
+
+extern "C" int fib_op_enforce_boundary(int device, const float* x, int h, int w, float* out) {
+  if (!x || !out) return fail(FIB_E_ARG, "NULL argument");
+  if (h < 3 || w < 3) return fail(FIB_E_ARG, "plane %dx%d too small: the boundary needs >= 3x3", h, w);
+  if (h > 65535) return fail(FIB_E_ARG, "op-level planes are limited to 65535 rows");
+  int r = op_device(device);
+  if (r) return r;
+  DevGuard dg(device);
+  const size_t n = (size_t)h * w;
+  DevBuf a, b;
+  CU(cudaMalloc(&a.p, n * sizeof(float)));
+  CU(cudaMalloc(&b.p, n * sizeof(float)));
+  CU(cudaMemcpy(a.p, x, n * sizeof(float), cudaMemcpyHostToDevice));
+  op_enforce_kernel<<<dim3((w + 127) / 128, h), 128>>>(a.p, h, w, b.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, b.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int fib_op_laplace(int device, const float* x, const float* phase, int h, int w, int mode, float* out) {
+  if (!x || !out) return fail(FIB_E_ARG, "NULL argument");
+  if (mode < 0 || mode > 2) return fail(FIB_E_ARG, "unknown mode %d", mode);
+  if (mode == 2 && !phase) return fail(FIB_E_ARG, "mode 2 (phase term) needs a phase field");
+  if (h < 3 || w < 3) return fail(FIB_E_ARG, "plane %dx%d too small", h, w);
+  if (h > 65535) return fail(FIB_E_ARG, "op-level planes are limited to 65535 rows");
+  int r = op_device(device);
+  if (r) return r;
+  DevGuard dg(device);
+  const size_t n = (size_t)h * w;
+  DevBuf a, b, ph;
+  CU(cudaMalloc(&a.p, n * sizeof(float)));
+  CU(cudaMalloc(&b.p, n * sizeof(float)));
+  CU(cudaMemcpy(a.p, x, n * sizeof(float), cudaMemcpyHostToDevice));
+  if (phase) {
+    CU(cudaMalloc(&ph.p, n * sizeof(float)));
+    CU(cudaMemcpy(ph.p, phase, n * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  op_laplace_kernel<<<dim3((w + 127) / 128, h), 128>>>(a.p, ph.p, h, w, mode, b.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, b.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int fib_op_rush_larsen(int device, const float* g, const float* g_inf, const float* tau, size_t n,
+                                  float dt, int strict, float* out) {
+  if (!g || !g_inf || !tau || !out) return fail(FIB_E_ARG, "NULL argument");
+  if (n == 0) return 0;
+  int r = op_device(device);
+  if (r) return r;
+  DevGuard dg(device);
+  DevBuf a, b, t, o;
+  for (DevBuf* d : {&a, &b, &t, &o}) CU(cudaMalloc(&d->p, n * sizeof(float)));
+  CU(cudaMemcpy(a.p, g, n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(b.p, g_inf, n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t.p, tau, n * sizeof(float), cudaMemcpyHostToDevice));
+  op_rush_larsen_kernel<<<(unsigned)((n + 255) / 256), 256>>>(a.p, b.p, t.p, n, -dt, strict, o.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, o.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 //   * only the diffusing variable is ping-ponged (xin -> xout); every other plane is updated in
 //     place, so the algorithmic traffic is exactly one read + one write per state variable.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "fib_stencil.cuh"
@@ -58,6 +59,12 @@ constexpr long kSmallGridCells = 320L * 1024;
 inline bool& pdl_enabled() {
   static thread_local bool on = true;
   return on;
+}
+// the flavour launched last on this thread (fib_last_kernel): tests use it to prove which
+// instantiation -- cells per thread, marching depth -- they compared with the oracle
+inline char* last_kernel_name() {
+  static thread_local char name[160] = "";
+  return name;
 }
 
 template <class M, int VEC, int R, int BY, bool PHASE>
@@ -172,6 +179,8 @@ inline cudaError_t launch_step_r(const Geom& g, const StepArgs<M>& a, cudaStream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (FIB_NC_LOADS == 0 && pdl && pdl_enabled()) ? 1 : 0;   // see fib_common.cuh
+  snprintf(last_kernel_name(), 160, "step_kernel<%s,VEC=%d,R=%d,BY=%d,PHASE=%d>", M::name(), VEC, R, BY,
+           PHASE ? 1 : 0);
   return cudaLaunchKernelEx(&cfg, step_kernel<M, VEC, R, BY, PHASE>, g, a);
 }
 

@@ -173,7 +173,26 @@ __device__ __forceinline__ float br_poly8(const float* __restrict__ c, float x) 
   return r;
 }
 
-template <bool CHEBY, bool SLOW>
+// strict-order evaluation of the reference's polynomial gates (br.py:215, 289-301, 327-331): x by an
+// fp32 DIVISION, S_i = (2x) S_{i-1}, r = d_0 + d_1 S_1 + ... left to right with one rounding per
+// multiply and per add (no FMA), then ionic.py:115-123 with IEEE division, libm expm1f and unfused
+// multiply / add.  d = the fp32-rounded table coefficients, unscaled.  This is the reference's own
+// operation sequence; the only thing left to differ is the last bit of expm1f (CUDA libm vs glibc).
+__device__ __forceinline__ float br_strict_eval(const float* __restrict__ d, const float (&S)[9]) {
+  float r = __fadd_rn(d[0], __fmul_rn(d[1], S[1]));
+#pragma unroll
+  for (int i = 2; i <= 8; ++i) r = __fadd_rn(r, __fmul_rn(d[i], S[i]));
+  return r;
+}
+__device__ __forceinline__ float rush_larsen_strict(float g, float g_inf, float tau, float neg_dt) {
+  const float e = expm1f(__fdiv_rn(neg_dt, tau));
+  return clip_tf(__fadd_rn(g, __fmul_rn(__fsub_rn(g, g_inf), e)), 0.00001f, 0.99999f);
+}
+
+// CHEBY: 0 = exact gates (br.py:175-205), 1 = polynomial gates by Horner's scheme (default for
+// config 'cheby'), 2 = polynomial gates in the reference's strict operation order (config
+// 'cheby_strict', FIB_F_CHEBY_STRICT)
+template <int CHEBY, bool SLOW>
 struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
   static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
@@ -182,10 +201,10 @@ struct BeelerReuter {
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
-      SLOW ? (CHEBY ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
+      SLOW ? (CHEBY == 1 ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
   // the one-cell-per-thread flavour of small grids keeps 6 (512^2 + hole: 45.7 vs 44.2 at 7)
   static __host__ __device__ constexpr int min_blocks(int vec) {
-    return (SLOW && CHEBY && vec == 1) ? 6 : MIN_BLOCKS;
+    return (SLOW && CHEBY == 1 && vec == 1) ? 6 : MIN_BLOCKS;
   }
   static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = false; // everything sees V0 = enforce_boundary(V) (br.py:128)
@@ -194,12 +213,18 @@ struct BeelerReuter {
   // slow gates J, D, F, XI are frozen when n == 0 (br.py:199-203): not even written back
   static __host__ __device__ constexpr bool stores(int k) { return k <= 2 || SLOW; }
   static size_t smem_bytes() { return 0; }
+  static const char* name() {
+    return CHEBY == 2 ? (SLOW ? "BeelerReuter<strict,slow>" : "BeelerReuter<strict,fast>")
+         : CHEBY == 1 ? (SLOW ? "BeelerReuter<cheby,slow>" : "BeelerReuter<cheby,fast>")
+                      : (SLOW ? "BeelerReuter<exact,slow>" : "BeelerReuter<exact,fast>");
+  }
   struct Params {
     float dt;            // fp32(dt)
     float neg_dt;        // fp32(-dt)                  m, h
     float neg_dt_slow;   // fp32(-(dt*n))              xi, j, d, f when n > 0 (br.py:197-200)
     float ddt;           // fp32(diff*dt)
     float poly[12][9];   // FIB_TABLE_BR_CHEBY re-expressed as monomial coefficients c_i = d_i 2^(i-1)
+                         // (CHEBY == 2: the table's own d_i, fp32)
   };
   static __device__ __forceinline__ void prologue(const StepArgs<BeelerReuter>&) {}
 
@@ -211,7 +236,29 @@ struct BeelerReuter {
     // (The polynomial flavour computes k AFTER its gates: hoisting it costs that kernel 10 %.)
     float k, rk;
 
-    if (CHEBY) {
+    if (CHEBY == 2) {
+      const float x = __fdiv_rn(__fsub_rn(V0, -30.0f), 60.0f);      // br.py:215
+      const float tx = __fmul_rn(2.0f, x);                          // br.py:299: T = 2*x*Ts[-1]
+      float S[9];
+      S[0] = 1.0f;
+      S[1] = x;
+#pragma unroll
+      for (int i = 2; i <= 8; ++i) S[i] = __fmul_rn(tx, S[i - 1]);
+#define FIB_BR_GATE(g, idx, ndt)                                                            \
+  s[idx] = rush_larsen_strict(s[idx], br_strict_eval(p.poly[2 * (g)], S),                  \
+                              br_strict_eval(p.poly[2 * (g) + 1], S), ndt)
+      FIB_BR_GATE(1, 1, p.neg_dt);                                 // m
+      FIB_BR_GATE(2, 2, p.neg_dt);                                 // h
+      if (SLOW) {
+        FIB_BR_GATE(0, 6, p.neg_dt_slow);                          // xi
+        FIB_BR_GATE(3, 3, p.neg_dt_slow);                          // j
+        FIB_BR_GATE(4, 4, p.neg_dt_slow);                          // d
+        FIB_BR_GATE(5, 5, p.neg_dt_slow);                          // f
+      }
+#undef FIB_BR_GATE
+      k = m_exp(0.04f * V0);
+      rk = m_rcp(k);
+    } else if (CHEBY == 1) {
       // x = (V0 - 0.5(max+min)) / (0.5(max-min)) = (V0 + 30)/60   (br.py:215)
       const float x = (V0 + 30.0f) * (1.0f / 60.0f);
 #define FIB_BR_GATE(RL, g, idx, ndt) \
@@ -263,7 +310,7 @@ struct BeelerReuter {
     const float sing = m_div(d23, one_m_e);
     const float iK1 = 0.35f * (m_div(4.f * fmaf(k, E85, -1.f), fmaf(k53, k53, k53)) + 0.2f * sing);
         // measured: reusing 1/k is +3 % for the six-gate polynomial step, -1.5 % for its two-gate one
-    const float ix1 = (SLOW || !CHEBY)
+    const float ix1 = (SLOW || CHEBY != 1)
                           ? XI * 0.8f * (fmaf(k, E77, -1.f) * (rk * (1.0f / E35)))
                           : XI * 0.8f * m_div(fmaf(k, E77, -1.f), k * E35);
     const float iNa = (4.0f * M * M * M * H * J + 0.005f) * (V0 - 50.0f);

@@ -278,6 +278,13 @@ struct Courtemanche {
                        : (MODE == COURT_ALL ? true : (MODE == COURT_FAST ? is_fast(k) : !is_fast(k)));
   }
   static size_t smem_bytes() { return 0; }
+  static const char* name() {
+    static const char* n[3][2][2] = {
+        {{"Courtemanche<fast>", "Courtemanche<fast,us>"}, {"Courtemanche<fast,lut>", "Courtemanche<fast,lut,us>"}},
+        {{"Courtemanche<slow>", "Courtemanche<slow,us>"}, {"Courtemanche<slow,lut>", "Courtemanche<slow,lut,us>"}},
+        {{"Courtemanche<all>", "Courtemanche<all,us>"}, {"Courtemanche<all,lut>", "Courtemanche<all,lut,us>"}}};
+    return n[MODE][LUT ? 1 : 0][US ? 1 : 0];
+  }
   struct Params {
     float dt_fast, neg_dt_fast;   // V, _Na_i_, _m_, _h_        (court.py:118-120)
     float dt_slow, neg_dt_slow;   // everything else: 10*dt for court.py, dt for court_ultra.py

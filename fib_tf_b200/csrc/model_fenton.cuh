@@ -24,6 +24,7 @@ struct Fenton4v {
   static constexpr bool STORE_X = true;
   static __host__ __device__ constexpr bool stores(int) { return true; }
   static size_t smem_bytes() { return 0; }
+  static const char* name() { return "Fenton4v"; }
   struct Params {
     float dt;    // fp32(dt)
     float ddt;   // fp32(diff * dt), folded in double like the reference (fenton.py:103)

@@ -59,7 +59,7 @@ class Fenton4v(IonicModel):
         if want is None:
             want = os.environ.get('FIB_STEPS_PER_LAUNCH')
         if want is None:
-            floor = self.FUSE_MIN_CELLS if self.phase is None else self.FUSE_MIN_CELLS_PHASE
+            floor = self.FUSE_MIN_CELLS if self._phase_rows is None else self.FUSE_MIN_CELLS_PHASE
             want = 2 if self.height * self.width >= floor else 1
         able = self.width % 4 == 0 and \
             (self._nranks == 1 or self.height // self._nranks >= 2)

@@ -20,6 +20,15 @@ Extra, optional config keys (all default to the reference's behaviour):
     graph        replay one CUDA graph per run() iteration (default True)
     distributed  row-shard the grid over the torch.distributed world (default False)
     lut          Courtemanche: V-only intermediates from the 150x30 table (default False)
+    probe_batch  headless runs with a cl_observer: the cycle-length probe is recorded on the device
+                 every iteration and read back once per `probe_batch` iterations (default 16; the
+                 observer is then called up to that many iterations late, with the reference's
+                 arguments; 1 = read it back every iteration like the reference)
+
+Collective calls under config['distributed'] (every rank must make them, in the same order):
+define(), run() (each iteration), fire_op(), image(), pot().eval() / _State[..].eval(),
+var[r, c].eval(), masked_image_mean(), excitable_fraction(), close().  cl_observer callbacks run on
+the rank that owns row 20 only and therefore must not call any of these.
 """
 import json
 import os
@@ -69,9 +78,11 @@ class IonicModel:
     MODEL_ID = None         # set by subclasses
 
     def __init__(self, config):
+        self._nranks = 1
+        self._phase_rows, self._phase_full, self._holes = None, None, []
         for key, val in config.items():     # ionic.py:35-37
-            setattr(self, key, val)
-        self.phase = None
+            if key != 'phase':
+                setattr(self, key, val)
         self._ops = {}
         self.defined = False
         self.dt_per_step = 1
@@ -89,25 +100,94 @@ class IonicModel:
         # (two halo rows: what the two-steps-per-launch kernel needs; one would do otherwise)
         self._phase_row0 = max(self._row0 - 2, 0)
         self._phase_row1 = min(self._row0 + self._rows + 2, self.height)
+        if config.get('phase') is not None:
+            self.phase = config['phase']
 
-    # ---- the reference's graph-building helpers have no meaning without TensorFlow ----------
-    def _no_graph(self, name):
-        raise NotImplementedError(
-            'IonicModel.%s built TensorFlow graph nodes in the reference (ionic.py); in fib_tf_b200 '
-            'the stencil and the ionic update are fused CUDA kernels selected by the model class. '
-            'Custom TensorFlow-expressed models are out of scope.' % name)
+    # ---- the reference's stencil helpers, as EAGER device ops on NumPy planes -----------------
+    # In the reference these build TensorFlow graph nodes; the fused step kernels never call them.
+    # They exist so that the stencil arithmetic can be used and checked in isolation (the same
+    # device functions as the step kernels: fib_stencil.cuh / fib_common.cuh).
+    def _op_device(self):
+        d = self.__dict__.get('device')
+        return int(d) if d is not None else 0
 
     def laplace(self, X0):
-        self._no_graph('laplace')
+        """REFLECT-pad X0 by one cell, 9-point stencil, plus the phase-field correction when a
+        phase field is defined (ionic.py:44-60).  X0: [height, width] array -> same shape."""
+        return _capi.op_laplace(X0, self._phase_plane(np.shape(X0)), 0, self._op_device())
 
     def phase_field(self, X):
-        self._no_graph('phase_field')
+        """The phase-field correction alone (ionic.py:70-81).  Like the reference it takes the
+        REFLECT-padded plane X [height+2, width+2] and returns [height, width]."""
+        X = np.asarray(X, dtype=np.float32)
+        inner = X[1:-1, 1:-1]
+        ph = self._phase_plane(inner.shape)
+        if ph is None:
+            raise AssertionError('phase_field needs a phase field (add_hole_to_phase_field)')
+        if not np.array_equal(np.pad(inner, 1, mode='reflect'), X):
+            raise ValueError('phase_field expects the REFLECT-padded plane, as laplace() passes it')
+        return _capi.op_laplace(inner, ph, 2, self._op_device())
 
     def enforce_boundary(self, X):
-        self._no_graph('enforce_boundary')
+        """Border ring := SYMMETRIC pad of the interior (ionic.py:107-113)."""
+        return _capi.op_enforce_boundary(X, self._op_device())
 
     def rush_larsen(self, g, g_inf, g_tau, dt, name=None):
-        self._no_graph('rush_larsen')
+        """clip(g + (g - g_inf) * expm1(-dt / g_tau), 1e-5, 0.99999) (ionic.py:115-123)."""
+        return _capi.op_rush_larsen(g, g_inf, g_tau, dt, False, self._op_device())
+
+    def _phase_plane(self, shape):
+        ph = self.phase
+        if ph is None:
+            return None
+        if tuple(ph.shape) != tuple(shape):
+            raise ValueError('plane shape %r does not match the phase field %r' % (tuple(shape), ph.shape))
+        return ph
+
+    # ---- the phase field: full grid for the user, local rows for the device -------------------
+    @property
+    def phase(self):
+        """[height, width] phase field or None, as in the reference (drivers do
+        `model.image() * model.phase`).  A sharded model keeps only its own rows (+2 halo rows)
+        for the device and builds the full-grid array on first use from the recorded holes."""
+        rows = self.__dict__.get('_phase_rows')
+        if rows is None:
+            return None
+        if self._nranks == 1:
+            return rows
+        if self.__dict__.get('_phase_full') is None:
+            full = None
+            for (x, y, radius, neg) in self._holes:
+                full = self._apply_hole(full, 0, self.height, x, y, radius, neg)
+            self._phase_full = full
+        return self._phase_full
+
+    @phase.setter
+    def phase(self, value):
+        if value is None:
+            self._phase_rows, self._phase_full, self._holes = None, None, []
+            return
+        a = np.asarray(value, dtype=np.float32)
+        if a.shape != (self.height, self.width):
+            raise ValueError('phase must be [height, width] = %r' % ((self.height, self.width),))
+        if self.__dict__.get('defined'):
+            raise AssertionError('the phase field must be set before calling define')
+        self._holes = None                      # no longer described by holes
+        self._phase_full = a if self._nranks > 1 else None
+        self._phase_rows = a[self._phase_row0:self._phase_row1] if self._nranks > 1 else a
+
+    def _apply_hole(self, phase, r0, r1, x, y, radius, neg):
+        """ionic.py:95-105 on global rows [r0, r1)."""
+        if phase is None:
+            phase = np.ones([r1 - r0, self.width], dtype=np.float32)
+        xx, yy = np.meshgrid(np.arange(self.width), np.arange(r0, r1))
+        dist = np.hypot(xx - x, yy - y)
+        if neg:
+            phase *= np.array(0.5 * (np.tanh(0.1 * (radius - dist)) + 1.0), dtype=np.float32)
+        else:
+            phase *= np.array(0.5 * (np.tanh(dist - radius) + 1.0), dtype=np.float32)
+        # floor at 1e-5 to avoid division by 0 in the phase-field term (ionic.py:104-105)
+        return np.maximum(phase, 1e-5)
 
     # ---- geometry (ionic.py:83-105) ----------------------------------------------------------
     def add_hole_to_phase_field(self, x, y, radius, neg=False):
@@ -115,17 +195,12 @@ class IonicModel:
         neg=True the inside is kept and the outside excluded.  Must precede define()."""
         if self.defined:
             raise AssertionError('add_hole_to_phase_field should be called before calling define')
-        r0, r1 = self._phase_row0, self._phase_row1
-        if self.phase is None:
-            self.phase = np.ones([r1 - r0, self.width], dtype=np.float32)
-        xx, yy = np.meshgrid(np.arange(self.width), np.arange(r0, r1))
-        dist = np.hypot(xx - x, yy - y)
-        if neg:
-            self.phase *= np.array(0.5 * (np.tanh(0.1 * (radius - dist)) + 1.0), dtype=np.float32)
-        else:
-            self.phase *= np.array(0.5 * (np.tanh(dist - radius) + 1.0), dtype=np.float32)
-        # floor at 1e-5 to avoid division by 0 in the phase-field term (ionic.py:104-105)
-        self.phase = np.maximum(self.phase, 1e-5)
+        if self._holes is None:
+            raise AssertionError('the phase field was assigned directly; holes cannot be added to it')
+        self._phase_rows = self._apply_hole(self._phase_rows, self._phase_row0, self._phase_row1,
+                                            x, y, radius, neg)
+        self._holes.append((x, y, radius, neg))
+        self._phase_full = None
 
     # ---- device context ---------------------------------------------------------------------
     def _make_context(self, flags=0, steps_per_launch=0):
@@ -139,8 +214,8 @@ class IonicModel:
         ctx = _capi.Context(self.MODEL_ID, self.height, self.width, self.dt, self.diff, flags=flags,
                             device=device, row0=self._row0 if sharded else 0,
                             rows=self._rows if sharded else 0, steps_per_launch=steps_per_launch)
-        if self.phase is not None:
-            ctx.set_phase(np.asarray(self.phase, dtype=np.float32), self._phase_row0)
+        if self._phase_rows is not None:
+            ctx.set_phase(np.asarray(self._phase_rows, dtype=np.float32), self._phase_row0)
         if sharded:
             import torch.distributed as dist
             box = [_capi.comm_unique_id() if self._rank == 0 else None]
@@ -216,28 +291,56 @@ class IonicModel:
         plot_every = max(int(self.dt_per_plot / self.dt_per_step), 1)
         watch = bool(im) or self.cl_observer is not None
         prow, pcol = 20, self.width // 2                         # ionic.py:216
-        for i in range(self.samples):
-            self._ctx.step(self.ode_op(i), 1)
-            yield i
-            if watch and i % plot_every == 0:
-                if im:
+        # Headless watching: the owner rank of row 20 records the probe cell on the device after every
+        # iteration (fib_probe_watch: a node of the iteration's CUDA graph) and reads the ring back once
+        # per `probe_batch` iterations -- no host round trip per iteration.
+        owner = self._row0 <= prow < self._row0 + self._rows
+        ring = watch and not im and owner
+        batch = max(1, min(int(self.__dict__.get('probe_batch', 16)), _capi.PROBE_RING))
+        unread = []                                              # iterations recorded, not yet read
+
+        def crossing(i, v1):
+            nonlocal v0, last_spike
+            if v1 >= 0.5 and v0 < 0.5:
+                cl = (i - last_spike) * self.dt_per_step * self.dt
+                if self.cl_observer is None:
+                    print('wavefront reaches the middle top point at %d, cycle length is %d' % (i, cl))
+                else:
+                    self.cl_observer(i, cl)
+                last_spike = i
+            v0 = v1
+
+        def drain():
+            vals = self._ctx.probe_fetch(len(unread)) if unread else []
+            if len(vals) != len(unread):
+                raise RuntimeError('probe ring returned %d values for %d iterations' % (len(vals), len(unread)))
+            w = self._probe_weight(prow, pcol)
+            for k, raw in zip(unread, vals):
+                if k % plot_every == 0:
+                    crossing(k, self._normalise(float(raw)) * w)
+            del unread[:]
+
+        if ring:
+            self._ctx.probe_watch(self._pot_name, prow, pcol)
+        try:
+            for i in range(self.samples):
+                self._ctx.step(self.ode_op(i), 1)
+                yield i
+                if ring:
+                    unread.append(i)
+                    if len(unread) >= batch:
+                        drain()
+                elif im and i % plot_every == 0:
                     image = self.image()
                     if self.phase is not None:
                         image *= self.phase
                     im.imshow(image)
-                    v1 = image[prow, pcol]
-                elif self._row0 <= prow < self._row0 + self._rows:
-                    v1 = self._probe_image(prow, pcol)      # headless: the owner rank watches
-                else:
-                    continue
-                if v1 >= 0.5 and v0 < 0.5:
-                    cl = (i - last_spike) * self.dt_per_step * self.dt
-                    if self.cl_observer is None:
-                        print('wavefront reaches the middle top point at %d, cycle length is %d' % (i, cl))
-                    else:
-                        self.cl_observer(i, cl)
-                    last_spike = i
-                v0 = v1
+                    crossing(i, image[prow, pcol])
+            if ring:
+                drain()
+        finally:
+            if ring and self._ctx is not None:
+                self._ctx.probe_watch(self._pot_name, -1, -1)
         if keep_state:                                           # ionic.py:226-229
             self.state = {}
             for s in self._State:
@@ -252,9 +355,12 @@ class IonicModel:
     def _probe_image(self, row, col):
         v = float(self._ctx.probe(self._pot_name, row, col))
         v = self._normalise(v)
-        if self.phase is not None and self._phase_row0 <= row < self._phase_row1:
-            v *= float(self.phase[row - self._phase_row0, col])
-        return v
+        return v * self._probe_weight(row, col)
+
+    def _probe_weight(self, row, col):
+        if self._phase_rows is not None and self._phase_row0 <= row < self._phase_row1:
+            return float(self._phase_rows[row - self._phase_row0, col])
+        return 1.0
 
     def _normalise(self, v):
         return (v - self.min_v) / (self.max_v - self.min_v)
@@ -336,6 +442,22 @@ class IonicModel:
         if self.MODEL_ID != _capi.FENTON4V:
             swx = (swx - self.min_v * sw) / (self.max_v - self.min_v)
         return swx / (self.height * self.width)
+
+    def excitable_fraction(self, cutoff=0.2, phase_min=1e-3):
+        """rho of court_ultra.py:504-509: np.sum(image[phase > phase_min] < cutoff) /
+        np.sum(phase > phase_min) with image = self.image(), as one threshold-count reduction on the
+        device (summed over ranks when sharded) -- no frame leaves the GPU."""
+        if self.MODEL_ID == _capi.FENTON4V:
+            sub, div = 0.0, 1.0
+        else:
+            sub, div = float(self.min_v), float(self.max_v - self.min_v)
+        below, total = self._ctx.count_below(self._pot_name, sub, div, cutoff, phase_min)
+        if self._nranks > 1:
+            import torch.distributed as dist
+            parts = [None] * self._nranks
+            dist.all_gather_object(parts, (below, total))
+            below, total = sum(p[0] for p in parts), sum(p[1] for p in parts)
+        return below / total if total else float('nan')
 
     def nonfinite_cells(self):
         """{variable: count} of NaN/Inf cells in this shard (empty dict when the state is healthy):

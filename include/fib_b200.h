@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FIB_ABI_VERSION 1
+#define FIB_ABI_VERSION 2
 
 typedef struct fib_ctx fib_ctx;
 
@@ -59,6 +59,12 @@ typedef enum {
 #define FIB_F_NO_GRAPH   0x20u  /* launch kernels directly instead of replaying a CUDA graph         */
 #define FIB_F_NO_CLIP    0x40u  /* Courtemanche: no [1e-5, 0.99999] clip of the Rush-Larsen gates, as in
                                    the native integrate_gate (courtemanche.h:287-292); court.py clips   */
+
+#define FIB_F_CHEBY_STRICT 0x80u /* BR + FIB_F_CHEBY: evaluate the polynomial gates in the reference's own
+                                   operation order (fp32 division for x, S_i recurrence, left-to-right
+                                   d_i*S_i sum, unfused Rush-Larsen with IEEE division and libm expm1f;
+                                   br.py:215,289-301,327-331, ionic.py:115-123) instead of Horner's scheme */
+#define FIB_F_NO_PERSIST 0x100u /* never use the persistent on-chip kernel (fib_persist.cuh) for small grids */
 
 typedef struct {
   uint32_t struct_size;      /* = sizeof(fib_config), for ABI evolution                              */
@@ -117,6 +123,10 @@ int fib_get_state(fib_ctx *ctx, int var, float *host, size_t n);
  * of grids too large to stage on the host in one piece); global coordinates, dense host block */
 int fib_get_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float *host);
 int fib_set_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host);
+/* enqueue-only variant of fib_set_rect: `host_pinned` (page-locked, fib_host_alloc) must stay valid and
+ * unchanged until the next fib_sync / synchronous call; the copy is ordered before every later call on
+ * this context.  Lets a caller stream a large initial state strip by strip without a round trip each. */
+int fib_set_rect_async(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host_pinned);
 
 /* asynchronous frame grab (the cube.npy writer of fenton.py:179-187 without stalling the stepper):
  * fib_snapshot_begin enqueues a device-side copy of the plane (ordered after everything already
@@ -151,6 +161,10 @@ int fib_step(fib_ctx *ctx, int op, int n_iter);
  * multi-GPU decomposition on one device and for single-process multi-GPU. */
 int fib_step_group(fib_ctx **ctxs, int n, int op, int n_iter);
 
+/* name of the step-kernel flavour (model, cells per thread, marching depth, phase flag) launched last
+ * by fib_step / fib_step_group on this thread: lets tests prove which instantiation they compared. */
+int fib_last_kernel(char *buf, size_t n);
+
 /* ---- stimulus: replaces pot().assign(tf.maximum(pot(), s)) (ionic.py:144-163) -----------
  * X := max(X, inside [r0,r1)x[c0,c1) ? value : floor_v) over the whole plane, GLOBAL coords. */
 int fib_stimulate(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float value,
@@ -170,6 +184,37 @@ int fib_count_nonfinite(fib_ctx *ctx, int var, uint64_t *count);
  * (0..3; must cover this shard); fib_masked_sum returns sum(mask*x) and sum(mask) over the shard. */
 int fib_set_weights(fib_ctx *ctx, int slot, const float *rows_host, int first_row, int nrows);
 int fib_masked_sum(fib_ctx *ctx, int var, int slot, double *sum_wx, double *sum_w);
+
+/* device-side observers, so that a headless run never moves a frame to the host:
+ * fib_probe_watch registers ONE cell (the cycle-length probe image[20, W//2] of ionic.py:216-224; global
+ * coordinates, must lie in this shard); from then on every fib_step iteration appends the cell's value to
+ * a device ring buffer (inside the iteration's CUDA graph: no host round trip).  fib_probe_fetch copies
+ * the values recorded since the last fetch (oldest first, at most `max`) and returns their number in *n;
+ * synchronous.  More than FIB_PROBE_RING unfetched values: the oldest are lost, *n reports what is left.
+ * row < 0 removes the watch. */
+#define FIB_PROBE_RING 4096
+int fib_probe_watch(fib_ctx *ctx, int var, int row, int col);
+int fib_probe_fetch(fib_ctx *ctx, float *out, size_t max, size_t *n);
+/* excitable fraction rho of court_ultra.py:504-509, np.sum(image[phase > w_min] < cutoff) /
+ * np.sum(phase > w_min) with image = (x - sub) / div: *below = cells with weight > w_min and image <
+ * cutoff, *total = cells with weight > w_min (weight = phase field, 1 if none).  Synchronous. */
+int fib_count_below(fib_ctx *ctx, int var, float sub, float div, float cutoff, float w_min,
+                    uint64_t *below, uint64_t *total);
+
+/* ---- op-level entry points of IonicModel's helpers on dense host planes [h][w] (eager; used by the
+ * drop-in IonicModel.enforce_boundary / laplace / phase_field / rush_larsen and by the parity tests that
+ * check the stencil arithmetic in isolation).  Synchronous; `device` = CUDA ordinal.
+ *   fib_op_enforce_boundary  ionic.py:107-113  border ring := SYMMETRIC pad of the interior
+ *   fib_op_laplace           ionic.py:44-60    mode 0: REFLECT-pad `x` by one cell, 9-point stencil
+ *                                              (+ phase term ionic.py:70-81 when `phase` != NULL);
+ *                                              mode 1: the step kernels' collapsed index map on a RAW
+ *                                              plane, = laplace(enforce_boundary(x));
+ *                                              mode 2: only the phase-field term (ionic.py:70-81)
+ *   fib_op_rush_larsen       ionic.py:115-123  strict != 0: IEEE division, libm expm1f, unfused */
+int fib_op_enforce_boundary(int device, const float *x, int h, int w, float *out);
+int fib_op_laplace(int device, const float *x, const float *phase, int h, int w, int mode, float *out);
+int fib_op_rush_larsen(int device, const float *g, const float *g_inf, const float *tau, size_t n,
+                       float dt, int strict, float *out);
 
 /* ---- sync / timing / accounting ------------------------------------------------------------ */
 int fib_sync(fib_ctx *ctx);

@@ -27,6 +27,26 @@ void ref_deriv(float* state21, float* rate21, float dt, const float* table, int 
   cfg.chronic = chronic != 0;
   deriv<Courtemanche>(state21, rate21, cfg);
 }
+// `steps` forward-Euler steps state += dt * rate for n independent cells (states[n][21]); the last
+// increment dt * rate of every cell is left in incs[n][21].  A loop around the reference's deriv<>.
+void ref_euler_batch(float* states, float* incs, long n, int steps, float dt, const float* table, int chronic) {
+  Config cfg{};
+  cfg.dt = dt;
+  cfg.table = table;
+  cfg.chronic = chronic != 0;
+  for (long i = 0; i < n; ++i) {
+    float* st = states + i * 21;
+    float rate[21];
+    for (int s = 0; s < steps; ++s) {
+      deriv<Courtemanche>(st, rate, cfg);
+      for (int k = 0; k < 21; ++k) {
+        const float inc = dt * rate[k];
+        incs[i * 21 + k] = inc;
+        st[k] = st[k] + inc;
+      }
+    }
+  }
+}
 int ref_table_rows() { return Courtemanche::TABLE_ROWS; }
 int ref_table_cols() { return Courtemanche::TABLE_COLS; }
 }

@@ -112,7 +112,8 @@ def court_ref():
         L.ref_init_table.argtypes = [_FP]
         L.ref_init_cell.argtypes = [_FP, C.c_int]
         L.ref_deriv.argtypes = [_FP, _FP, C.c_float, _FP, C.c_int]
-        for f in (L.ref_calc_inter, L.ref_init_table, L.ref_init_cell, L.ref_deriv):
+        L.ref_euler_batch.argtypes = [_FP, _FP, C.c_long, C.c_int, C.c_float, _FP, C.c_int]
+        for f in (L.ref_calc_inter, L.ref_init_table, L.ref_init_cell, L.ref_deriv, L.ref_euler_batch):
             f.restype = None
         _ref = L
     return _ref

@@ -523,29 +523,107 @@ def var_floor(kind, name):
 
 def rel_err(got, ref, floor):
     """max |got - ref| / max(|ref|, floor): per-cell relative error with an absolute floor
-    (var_floor); the metric of SURVEY.md Appendix B.2."""
-    den = np.maximum(np.abs(ref), floor)
-    with np.errstate(invalid='ignore'):
-        return float(np.nanmax(np.abs(np.asarray(got, np.float64) - ref) / den))
+    (var_floor); the metric of SURVEY.md Appendix B.2.
+
+    Non-finite cells are NOT ignored: the NaN pattern and the infinities of `got` must equal the
+    reference's, otherwise the error is +inf (every assertion on it fails)."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    if got.shape != ref.shape:
+        raise ValueError('rel_err: shapes %r and %r differ' % (got.shape, ref.shape))
+    if got.size == 0:
+        return 0.0
+    bad_g, bad_r = ~np.isfinite(got), ~np.isfinite(ref)
+    if bad_g.any() or bad_r.any():
+        same = np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[bad_r & ~np.isnan(ref)],
+                                                                               ref[bad_r & ~np.isnan(ref)]) \
+            and np.array_equal(bad_g, bad_r)
+        if not same:
+            return float('inf')
+        got, ref = got[~bad_r], ref[~bad_r]
+        if got.size == 0:
+            return 0.0
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)))
 
 
 PARITY_RTOL = 1e-5      # north_star: 1e-5 relative per step over the first 100 steps
-NOISE_FACTOR = 3.0      # ... but never tighter than 3x the reference's own fp32 uncertainty
+NOISE_FACTOR = 3.0      # waived variables only: never tighter than 3x the reference's own fp32 uncertainty
+
+# The bar is a FLAT 1e-5 for every state variable of every model flavour, except the variables
+# named here.  For these the reference's own fp32 result is not defined to 1e-5: the fixtures record,
+# per plane, `noise` = how far the UNMODIFIED reference moves when only its fp32 math library is
+# swapped for another correctly-rounding one (oracle/tfshim.ALT_LIBM) and `rounding` = its distance
+# from the same graph evaluated in float64 (oracle/tfshim.WIDE); a waived variable is held to
+# min(cap, max(1e-5, 3 * max(noise, rounding))).  `why` is the mechanism; profiles/r2_parity_report.txt
+# lists the measured error of every variable of every fixture against the flat bar.
+WAIVERS = {
+    # degree-8 polynomial gates (br.py:207-252): the S-basis sum d_i 2^(i-1) x^i cancels ~4 digits
+    # (|d_i S_i| ~ 1e2 for a result ~1) and tau_h < 0 at rest makes the Rush-Larsen factor blow up
+    # into the clip: the reference's own libm swap moves M, H, D by 2-4e-5, its float64 evaluation
+    # by 1.2e-4.  'cheby' = Horner evaluation (the default), 'cheby_strict' = the reference's
+    # operation order (config['cheby_strict']).
+    'br/cheby': {'vars': ('M', 'H', 'J', 'D', 'XI'), 'cap': 4e-4, 'use': ('noise', 'rounding')},
+    'br/cheby_strict': {'vars': ('M', 'H', 'J', 'D', 'XI'), 'cap': 1.5e-4, 'use': ('noise',)},
+    # exact gates with the multi-rate schedule: D and XI advance with 5 dt in one Rush-Larsen step;
+    # the libm swap alone moves the reference by 1.4e-5 (D) / 4.7e-6 (XI)
+    'br/skip': {'vars': ('D', 'XI'), 'cap': 5e-5, 'use': ('noise', 'rounding')},
+    # Courtemanche: u and v relax towards 1/(1 + exp(-(Fn - 3.4175e-13)/1.367e-15)) (court.py:241-247),
+    # a sigmoid whose argument is a difference of ~1e-13 quantities scaled by 7e14: one ulp of Fn is
+    # ~1e-2 in the exponent.  The reference's libm swap moves them by 3e-5 ... 1e-4.
+    'court': {'vars': ('_u_', '_v_'), 'cap': 6e-4, 'use': ('noise', 'rounding')},
+}
+
+
+def flavour_of(kind, cfg):
+    """Key into WAIVERS for a model kind + config."""
+    if kind == 'br':
+        if cfg.get('cheby'):
+            return 'br/cheby_strict' if cfg.get('cheby_strict') else 'br/cheby'
+        return 'br/skip' if cfg.get('skip') else 'br/exact'
+    if kind in ('court', 'court_ultra'):
+        return 'court'
+    return kind
+
+
+def is_waived(kind, cfg, var):
+    w = WAIVERS.get(flavour_of(kind, cfg))
+    return bool(w) and var in w['vars']
+
+
+def tolerance(kind, cfg, var, noise=0.0, rounding=0.0):
+    """The parity bar (rel_err metric) of one state variable: 1e-5 flat, or -- for the variables
+    named in WAIVERS -- min(cap, max(1e-5, 3 * the reference's own uncertainty))."""
+    w = WAIVERS.get(flavour_of(kind, cfg))
+    if not w or var not in w['vars']:
+        return PARITY_RTOL
+    own = max(noise if 'noise' in w['use'] else 0.0, rounding if 'rounding' in w['use'] else 0.0)
+    return min(w['cap'], max(PARITY_RTOL, NOISE_FACTOR * own))
 
 
 def parity_tolerance(meta, key):
-    """Tolerance (in the rel_err metric) for snapshot plane `key` = 's{i}__{var}' of a fixture:
-        max(1e-5, 3 * max(noise, rounding))
-    noise    = deviation of the UNMODIFIED reference from itself when only its fp32 math library
-               is swapped for another correctly-rounding one (oracle/tfshim.ALT_LIBM);
-    rounding = deviation of the fp32 reference from the same graph evaluated in float64
-               (oracle/tfshim.WIDE): its total fp32 rounding error.
-    Both are recorded per plane in the fixture by oracle/make_golden.py.  Where the reference's
-    own fp32 result is only defined to 1e-4 (degree-8 polynomial gates in the ill-conditioned
-    scaled-monomial basis, the Courtemanche u/v release gates behind a 1e-15-wide sigmoid) no
-    second fp32 implementation can be asked to agree with it to 1e-5."""
-    own = max(meta.get('noise', {}).get(key, 0.0), meta.get('rounding', {}).get(key, 0.0))
-    return max(PARITY_RTOL, NOISE_FACTOR * own)
+    """Bar for snapshot plane `key` = 's{i}__{var}' of a golden fixture (see tolerance())."""
+    var = key.split('__', 1)[1]
+    return tolerance(meta['model'], meta['config'], var, meta.get('noise', {}).get(key, 0.0),
+                     meta.get('rounding', {}).get(key, 0.0))
+
+
+def model_uncertainty(metas, kind, cfg, var):
+    """Worst (noise, rounding) of `var` over the fixtures of the same flavour: the reference's own
+    uncertainty to use where no fixture exists for the exact run (live-oracle tests)."""
+    fl = flavour_of(kind, cfg)
+    if fl == 'br/cheby_strict':
+        fl = 'br/cheby'
+    n = r = 0.0
+    for meta in metas:
+        if flavour_of(meta['model'], meta['config']) != fl:
+            continue
+        for key, v in meta.get('noise', {}).items():
+            if key.split('__', 1)[1] == var:
+                n = max(n, v)
+        for key, v in meta.get('rounding', {}).items():
+            if key.split('__', 1)[1] == var:
+                r = max(r, v)
+    return n, r
 
 
 # --------------------------------------------------------------------------

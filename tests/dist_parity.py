@@ -49,6 +49,18 @@ def main():
                     m.fire_op('slow')
                 if i == 1:
                     m.fire_op('s2')
+            if i == 2:
+                # a rank-LOCAL host write: a block on the LAST rows of rank 0's shard, written only by
+                # rank 0 (fib_set_rect can only be called by the owner).  The neighbour's halo copy of
+                # those rows is stale until the next fib_step refreshes it -- which must happen on every
+                # rank without any rank-local knowledge (fib_capi.cu: refresh_halos_nccl).
+                sh = models[0]
+                pot = sh._pot_name
+                blk = np.full((2, 40), float(sh.max_v) * 0.3, np.float32)
+                r_edge = sh._rows - 2 if rank == 0 else None           # rank 0 owns rows [0, rows)
+                if rank == 0:
+                    sh._ctx.set_rect(pot, r_edge, 30, blk)
+                    models[1]._ctx.set_rect(pot, r_edge, 30, blk)
         for name in models[0]._ctx.var_names:
             full = models[0]._State[name].eval()          # gathered over ranks (collective)
             if rank == 0:

@@ -4,17 +4,17 @@
   (3) size-independent properties at the full benchmark sizes.
 
 Tolerance (written here, used everywhere below): for every state variable and snapshot,
-    rel_err = max |cuda - ref| / max(|ref|, floor(var))  <=  max(1e-5, 3 * noise)
+    rel_err = max |cuda - ref| / max(|ref|, floor(var))  <=  1e-5            (BASELINE.json's bar)
 (floor: 0.1 % of the variable's range; the full range for the accumulating voltage V of BR /
-Courtemanche -- see oracle.monodomain_np.var_floor)
-where `noise` = max(the reference's deviation from itself when ONLY its fp32 math library is
-swapped for another correctly-rounding one, the reference's total fp32 rounding error against the
-same graph evaluated in float64), both recorded per plane in the fixture (oracle/make_golden.py,
-oracle/tfshim.ALT_LIBM / WIDE).  1e-5 is BASELINE.json's per-step bar and it is what 4v and the
-exact-gate BR are held to; the noise term exists because the reference's OWN fp32 result is only
-defined to ~1e-4 for the degree-8 polynomial gates (ill-conditioned scaled-monomial basis) and for
-the Courtemanche u/v gates (a 1e-15-wide sigmoid): no second fp32 implementation can agree with it
-more closely than it agrees with exact arithmetic.  Never looser than 3x that."""
+Courtemanche -- see oracle.monodomain_np.var_floor; a NaN / Inf pattern that differs from the
+reference's is an infinite error).  The ONLY exceptions are the variables named in
+oracle.monodomain_np.WAIVERS -- the gates driven by the degree-8 polynomial fits of BR `cheby`
+(M, H, J, D, XI), D / XI of the exact-gate `skip` schedule and the Courtemanche release gates
+_u_ / _v_ -- for which the reference's OWN fp32 result moves by more than 1e-5 when only its math
+library is swapped (`noise`, recorded per plane in the fixtures by oracle/make_golden.py with
+oracle/tfshim.ALT_LIBM) or against float64 (`rounding`, tfshim.WIDE).  Those are held to
+min(cap, max(1e-5, 3 * that uncertainty)) with a hard cap per flavour.  The measured error of every
+variable against the flat bar is committed in profiles/r2_parity_report.txt."""
 import numpy as np
 import pytest
 
@@ -83,13 +83,13 @@ def test_long_horizon_apd_and_activation_time(cuda, name):
     assert np.max(np.abs(trace - arr['probe'])) <= 0.01 * (hi - lo)
 
 
-def model_noise(kind):
-    worst = 0.0
-    for n in SHORT:
-        meta, _ = load_fixture(n)
-        if meta['model'] == kind:
-            worst = max([worst] + list(meta['noise'].values()) + list(meta['rounding'].values()))
-    return worst
+METAS = [load_fixture(n)[0] for n in SHORT]
+
+
+def live_tolerance(kind, cfg, var):
+    """Bar for a run that has no fixture of its own: 1e-5, or for a waived variable the rule of
+    oracle.monodomain_np.tolerance with the worst uncertainty the fixtures of that flavour recorded."""
+    return onp.tolerance(kind, cfg, var, *onp.model_uncertainty(METAS, kind, cfg, var))
 
 
 @pytest.mark.parametrize('kind,cfg,iters', [
@@ -112,7 +112,6 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
         m.add_hole(W // 2, W // 2, 30 * W // 512)
         m.define()
         m.add_pace('s2', 'luq', 1.0 if kind == 'fenton4v' else 10.0)
-    tol = max(1e-5, 3 * model_noise(kind))
     for i in range(iters):
         for m in (ref, gpu):
             m.iterate()
@@ -122,6 +121,7 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
                 m.fire('s2')
     for v in ref.state:
         e = onp.rel_err(gpu.state[v], ref.state[v], onp.var_floor(kind, v))
+        tol = live_tolerance(kind, base, v)
         assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (kind, v, e, tol)
     gpu.close()
 
@@ -568,13 +568,14 @@ def test_beeler_reuter_removable_singularities(cuda, flags):
     inner = np.zeros((H, W), bool)
     inner[1:-1, 1:-1] = True                      # the border ring is overwritten by enforce_boundary
     keep = inner & ~near
-    # exact gates: measured worst 2.3e-5 (C of the cells that took the NaN path, 5 steps later);
-    # polynomial gates: the fixtures' own rounding noise (the S-basis sum, model_br.cuh)
-    tol = max(1e-5, 3 * model_noise('br')) if flags['cheby'] else 5e-5
+    # random states over the WHOLE voltage range, including where the polynomial fits are worst
+    # (tau_h < 0 below -83.85 mV) and the cells that took the NaN -> clip path: exact gates measured
+    # worst 2.3e-5 (C of those cells, 5 steps later), hence 5e-5; polynomial gates: the waiver caps
     for v in ref.state:
         got, want = gpu.state[v], ref.state[v]
         assert np.isfinite(got[inner]).all() and np.isfinite(want[inner]).all(), v
         e = onp.rel_err(got[keep], want[keep], onp.var_floor('br', v))
+        tol = max(5e-5, live_tolerance('br', cfg, v))
         assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (flags, v, e, tol)
     # the cells planted ON the singular points took the reference's NaN -> upper clip bound path
     on23 = inner & (V == np.float32(-23.0))

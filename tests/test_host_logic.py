@@ -99,9 +99,20 @@ def test_chebyshev_table_equals_oracle_and_reference_coefficients():
     assert list(a[4]) == [1, 0, -4, 0, 1, 0, 0, 0, 0] and list(a[8][::2]) == [1, -16, 20, -8, 1]
 
 
-def test_graph_builder_helpers_are_explicitly_out_of_scope():
-    with pytest.raises(NotImplementedError):
-        Fenton4v(CFG).laplace(None)
+def test_stencil_helpers_validate_before_touching_the_device():
+    """IonicModel.laplace / enforce_boundary / phase_field / rush_larsen are eager device ops
+    (fib_op_*); malformed arguments are refused on the host, before any CUDA call."""
+    from fib_tf_b200 import _capi
+    m = Fenton4v(CFG)
+    with pytest.raises(_capi.FibError):
+        m.laplace(None)
+    with pytest.raises(_capi.FibError):
+        m.enforce_boundary(np.zeros(5, np.float32))
+    with pytest.raises(AssertionError):
+        m.phase_field(np.zeros((CFG['height'] + 2, CFG['width'] + 2), np.float32))     # no phase field
+    m.add_hole_to_phase_field(10, 10, 3)
+    with pytest.raises(ValueError):
+        m.laplace(np.zeros((7, 9), np.float32))          # plane shape != phase shape
 
 
 def test_headless_screen_keeps_the_reference_protocol(tmp_path):

@@ -45,6 +45,22 @@ class RecordingContext:
     def step(self, op=0, n_iter=1):
         self.calls.append(('step', op, n_iter))
         self.launches += self.dt_per_step * n_iter
+        if self.watch and op == 0:              # the device records the watched cell per iteration
+            for _ in range(n_iter):
+                var, row, col = self.watch
+                self.ring.append(self.probe_script.pop(0) if self.probe_script else self.state[var][row, col])
+
+    watch, ring = None, None
+
+    def probe_watch(self, var, row, col):
+        self.calls.append(('watch', var, row, col))
+        self.watch, self.ring = ((var, row, col) if row >= 0 else None), []
+
+    def probe_fetch(self, max_values=4096):
+        self.calls.append(('fetch', max_values))
+        vals = self.ring[:max_values]
+        del self.ring[:len(vals)]
+        return np.asarray(vals, dtype=np.float32)
 
     def stimulate(self, var, r0, r1, c0, c1, value, floor_v):
         self.calls.append(('stim', var, r0, r1, c0, c1, value, floor_v))
@@ -125,7 +141,20 @@ def test_cycle_length_observer_without_a_screen(recording):
         pass
     assert [h[0] for h in hits] == [4, 40]
     assert hits[1][1] == pytest.approx((40 - 4) * 5 * 0.1)        # cycle length in ms (ionic.py:218)
-    assert all(c[2:] == (20, 32) for c in m._ctx.calls if c[0] == 'probe')
+    # the probe cell [20, W//2] is watched on the device and read back in batches of 16 iterations
+    calls = m._ctx.calls
+    assert ('watch', 'V', 20, 32) in calls and not [c for c in calls if c[0] == 'probe']
+    assert [c[1] for c in calls if c[0] == 'fetch'] == [16, 16, 16, 12]
+    assert calls[-2] == ('watch', 'V', -1, -1)
+    # probe_batch = 1: read back after every iteration, same observer calls
+    m = BeelerReuter(dict(CFG, duration=30, dt_per_plot=5, probe_batch=1))
+    m.define()
+    hits2 = []
+    m.cl_observer = lambda i, cl: hits2.append((i, cl))
+    RecordingContext.probe_script = [-80.0] * 4 + [0.0] * 10 + [-80.0] * 26 + [10.0] * 20
+    for _ in m.run(None):
+        pass
+    assert hits2 == hits and len([c for c in m._ctx.calls if c[0] == 'fetch']) == 60
 
 
 def test_courtemanche_slow_op_state_dict_and_timeline(recording, tmp_path):
@@ -162,7 +191,7 @@ def test_steps_per_launch_choice(recording, monkeypatch):
 
     def choice(width, height, hole=False, **extra):
         m = Fenton4v(dict(base, width=width, height=height, **extra))
-        m.phase = np.ones([2, 2], np.float32) if hole else None     # define() is not run: no arrays
+        m._phase_rows = np.ones([2, 2], np.float32) if hole else None     # define() is not run: no arrays
         m._nranks = 1
         return m._steps_per_launch()
 
