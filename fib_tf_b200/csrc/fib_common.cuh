@@ -66,31 +66,38 @@ template <> struct VecIO<4> {
 // 52), which happens to a few cells of a 512^2 grid in every repolarisation wave; on the GPU the
 // clip turns that NaN into the upper bound for one step and the run goes on (docs/br.png), whereas
 // NaN-propagating min/max (NumPy, TF on the CPU) would poison the whole grid within 50 ms.
-__device__ __forceinline__ float clip_tf(float x, float lo, float hi) {
-  return fmaxf(fminf(x, hi), lo);
+// (All of these are generic over T = float or f2, see fib_math.cuh.)
+template <class T> __device__ __forceinline__ T clip_tf(T x, float lo, float hi) {
+  return vmax(vmin(x, T(hi)), T(lo));
 }
 
 // IonicModel.rush_larsen (ionic.py:115-123): clip(g + (g - g_inf) * expm1(-dt / tau), 1e-5, 0.99999).
 // neg_dt = fp32(-dt) (or fp32(-(dt*n)) folded in double on the host, br.py:197-200).
-__device__ __forceinline__ float rush_larsen(float g, float g_inf, float tau, float neg_dt) {
-  float e = m_expm1_neg(m_div(neg_dt, tau));
-  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+template <class T> __device__ __forceinline__ T rush_larsen(T g, T g_inf, T tau, float neg_dt) {
+  const T e = m_expm1_neg(m_div(T(neg_dt), tau));
+  return clip_tf(vfma(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
 // Rush-Larsen with caller-supplied clip bounds: (1e-5, 0.99999) for the Python models, (-inf, +inf)
 // for the native courtemanche.h rule, which does not clip (courtemanche.h:287-292)
-__device__ __forceinline__ float rush_larsen_b(float g, float g_inf, float tau, float neg_dt, float lo,
-                                               float hi) {
-  const float e = m_expm1_neg(m_div(neg_dt, tau));
-  const float r = fmaf(g - g_inf, e, g);
+template <class T> __device__ __forceinline__ T rush_larsen_eb(T g, T g_inf, T e, float lo, float hi) {
+  const T r = vfma(g - g_inf, e, g);
   return lo == -INFINITY ? r : clip_tf(r, lo, hi);      // uniform select; no clip in native mode
 }
-__device__ __forceinline__ float rush_larsen_eb(float g, float g_inf, float e, float lo, float hi) {
-  const float r = fmaf(g - g_inf, e, g);
-  return lo == -INFINITY ? r : clip_tf(r, lo, hi);
+template <class T> __device__ __forceinline__ T rush_larsen_b(T g, T g_inf, T tau, float neg_dt, float lo,
+                                                              float hi) {
+  return rush_larsen_eb(g, g_inf, m_expm1_neg(m_div(T(neg_dt), tau)), lo, hi);
 }
 // same with e = expm1(-dt/tau) precomputed (Python-scalar tau: court.py:189,243)
-__device__ __forceinline__ float rush_larsen_e(float g, float g_inf, float e) {
-  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+template <class T> __device__ __forceinline__ T rush_larsen_e(T g, T g_inf, T e) {
+  return clip_tf(vfma(g - g_inf, e, g), 0.00001f, 0.99999f);
+}
+// the reference's operation sequence, unfused, IEEE division, libm expm1f (strict-order flavour)
+__device__ __forceinline__ float rush_larsen_strict(float g, float g_inf, float tau, float neg_dt) {
+  const float e = expm1f(__fdiv_rn(neg_dt, tau));
+  return clip_tf(__fadd_rn(g, __fmul_rn(__fsub_rn(g, g_inf), e)), 0.00001f, 0.99999f);
+}
+__device__ __forceinline__ f2 rush_larsen_strict(f2 g, f2 g_inf, f2 tau, float neg_dt) {
+  return f2(rush_larsen_strict(g.x, g_inf.x, tau.x, neg_dt), rush_larsen_strict(g.y, g_inf.y, tau.y, neg_dt));
 }
 
 }  // namespace fib

@@ -25,6 +25,7 @@ namespace fib {
 //   STORE_X       step writes the diffusing variable
 //   min_blocks(v) resident CTAs per SM the register allocator must leave room for, v cells per thread
 //   PREFETCH      prefetch the next marching row's lines into L1
+//   PACKED        with two cells per thread, run them as one f2 pair (packed fp32, fib_math.cuh)
 //   stores(k)     plane k is written by this step
 //   struct Params (uniform scalars / small tables; lives in the kernel parameter bank)
 //   cell(p, xraw, x0, lap, s[NS], xnew)
@@ -132,7 +133,7 @@ step_kernel(const Geom g, const StepArgs<M> a) {
 #pragma unroll
       for (int k = 0; k < M::NS; ++k) VecIO<VEC>::ld(a.s[k] + off, sv[k]);
 
-      float xnew[VEC];
+      float xnew[VEC], lapv[VEC];
 #pragma unroll
       for (int l = 0; l < VEC; ++l) {
         float lap = 0.f;
@@ -143,12 +144,31 @@ step_kernel(const Geom g, const StepArgs<M> a) {
             lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l], pS[l],
                                             pC[l], pC[l + 2], pC[l + 1]));
         }
-        float sl[M::NS > 0 ? M::NS : 1];
+        lapv[l] = lap;
+      }
+      if constexpr (M::PACKED && VEC == 2) {
+        // two cells per thread as ONE packed pair: every multiply-add of the ionic update is a single
+        // FFMA2 / FMUL2 / FADD2 for both cells (fib_math.cuh); per lane the arithmetic is that of the
+        // scalar flavour of the same source
+        f2 sp[M::NS > 0 ? M::NS : 1];
 #pragma unroll
-        for (int k = 0; k < M::NS; ++k) sl[k] = sv[k][l];
-        M::cell(a, xraw[l], xC[l + 1], lap, sl, xnew[l]);
+        for (int k = 0; k < M::NS; ++k) sp[k] = f2(sv[k][0], sv[k][VEC - 1]);
+        f2 xn;
+        M::cell(a, f2(xraw[0], xraw[VEC - 1]), f2(xC[1], xC[VEC]), f2(lapv[0], lapv[VEC - 1]), sp, xn);
+        xnew[0] = xn.x;
+        xnew[VEC - 1] = xn.y;
 #pragma unroll
-        for (int k = 0; k < M::NS; ++k) sv[k][l] = sl[k];
+        for (int k = 0; k < M::NS; ++k) { sv[k][0] = sp[k].x; sv[k][VEC - 1] = sp[k].y; }
+      } else {
+#pragma unroll
+        for (int l = 0; l < VEC; ++l) {
+          float sl[M::NS > 0 ? M::NS : 1];
+#pragma unroll
+          for (int k = 0; k < M::NS; ++k) sl[k] = sv[k][l];
+          M::cell(a, xraw[l], xC[l + 1], lapv[l], sl, xnew[l]);
+#pragma unroll
+          for (int k = 0; k < M::NS; ++k) sv[k][l] = sl[k];
+        }
       }
 #pragma unroll
       for (int k = 0; k < M::NS; ++k)

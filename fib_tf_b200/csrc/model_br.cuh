@@ -2,14 +2,17 @@
 // Restates br.py:125-173 (solve), :175-205 (exact gates), :207-252 (Chebyshev gates),
 // :255-273 (alpha/beta), :289-331 (scaled-monomial expansion), coefficients br.py:49-62.
 //
-// Instruction budget (this kernel is issue-bound, not HBM-bound): see fib_math.cuh.  Beyond the
-// few-ulp transcendental layer two algebraic identities are used, both exact in real arithmetic:
+// Instruction budget (this kernel is issue-bound, not HBM-bound): see fib_math.cuh.  The cell is
+// written once, generic over T = float (one cell per thread, small grids) and T = f2 (two cells per
+// thread, every multiply-add a packed FFMA2 / FMUL2 / FADD2).  Beyond the few-ulp transcendental
+// layer two algebraic identities are used, both exact in real arithmetic:
 //   * the six current exponentials of br.py:150-157 are all e^{0.04 V0} times a constant;
 //   * r = d0 + sum d_i S_i with S_i = 2^{i-1} x^i is the ordinary polynomial sum c_i x^i,
 //     c_i = d_i 2^{i-1} (exact scaling), evaluated by Horner's scheme with FMAs (8 per gate
 //     function).  This is MORE accurate than the reference's left-to-right
 //     fp32 sum in the ill-conditioned S basis; the two differ by the reference's own rounding
-//     error (recorded in the fixtures as meta['rounding']).
+//     error (recorded in the fixtures as meta['rounding']).  config['cheby_strict'] selects the
+//     reference's own operation order instead (CHEBY == 2 below).
 #pragma once
 #include "fib_kernels.cuh"
 
@@ -36,6 +39,7 @@ namespace fib {
 
 // (c0 e^{c1(v+c2)} + c3 (v+c4)) / (e^{c5(v+c2)} + c6)  -- br.py:255-264.  Called with literal
 // coefficients only, so every `== 0` test below folds at compile time (exp(0) == 1 exactly).
+// Scalar: the readable statement of the exact gates, used by the FIB_ACCURATE_MATH build.
 __device__ __forceinline__ float br_rate(float v, float c0, float c1, float c2, float c3, float c4,
                                          float c5, float c6) {
   const float e_num = (c1 == 0.f) ? 1.f : m_exp(c1 * (v + c2));
@@ -69,34 +73,34 @@ __device__ __forceinline__ void br_inf_rate_exact(float v, float& inf, float& ra
 }
 
 // rush_larsen with tau given as its reciprocal: expm1(-dt/tau) = expm1(-dt * rate)
-__device__ __forceinline__ float rush_larsen_rate(float g, float g_inf, float rate, float neg_dt) {
-  return rush_larsen_e(g, g_inf, m_expm1_neg(neg_dt * rate));
+template <class T> __device__ __forceinline__ T rush_larsen_rate(T g, T g_inf, T rate, float neg_dt) {
+  return rush_larsen_e(g, g_inf, m_expm1_neg(T(neg_dt) * rate));
 }
 
 // a = n1/d1, b = n2/d2 (all four positive): rate = a + b = (n1 d2 + n2 d1)/(d1 d2) and
 // inf = a/rate = n1 d2/(n1 d2 + n2 d1) -- two SFU reciprocals instead of three, no cancellation.
-__device__ __forceinline__ float rush_larsen_frac(float g, float n1, float d1, float n2, float d2,
-                                                  float neg_dt) {
-  const float n1d2 = n1 * d2;
-  const float N = fmaf(n2, d1, n1d2);
-  const float rate = N * m_rcp(d1 * d2);
+template <class T>
+__device__ __forceinline__ T rush_larsen_frac(T g, T n1, T d1, T n2, T d2, float neg_dt) {
+  const T n1d2 = n1 * d2;
+  const T N = vfma(n2, d1, n1d2);
+  const T rate = N * m_rcp(d1 * d2);
   return rush_larsen_rate(g, n1d2 * m_rcp(N), rate, neg_dt);
 }
 
-// The exact gates of br.py:175-205 / 255-273 for one cell, same formulas as br_inf_rate_exact
-// (which stays as the readable statement and is what tests/test_gpu_parity.py's accurate-math
-// build checks), with the SFU work trimmed -- the exact-gate kernel is MUFU-bound (~47 SFU ops per
-// cell): exponentials that differ only by a constant factor are computed once
+// The exact gates of br.py:175-205 / 255-273 for one cell (or a pair), same formulas as
+// br_inf_rate_exact (which stays as the readable statement and is what the accurate-math build
+// uses), with the SFU work trimmed -- the exact-gate kernel is MUFU-bound (~47 SFU ops per cell):
+// exponentials that differ only by a constant factor are computed once
 //   e^{-0.25(v+78)} = e^{-0.25(v+77)} e^{-0.25}          (alpha_j <- alpha_h)
 //   e^{-0.2(v+30)}  = e^{-0.2(v+78)} e^{9.6}              (beta_f  <- alpha_j)
 //   e^{-0.1(v+32)}  = e^{-0.1(v+47)} e^{1.5}              (beta_j  <- alpha_m)
 //   e^{-0.04(v+20)} = e^{-0.8} / e^{0.04 v}                (beta_xi <- the currents' k)
 // and the two-fraction gates use rush_larsen_frac.  m and h keep the reference's operation
 // structure, so V0 == -47.0f still yields the reference's 0/0 -> clip upper bound (fib_common.cuh).
-template <bool SLOW>
-__device__ __forceinline__ void br_gates_exact(float v, float rk, float (&s)[7], float neg_dt,
-                                               float neg_dt_slow) {
+template <bool SLOW, class T>
+__device__ __forceinline__ void br_gates_exact(T v, T rk, T (&s)[7], float neg_dt, float neg_dt_slow) {
 #if FIB_ACCURATE_MATH
+  static_assert(Lanes<T>::N == 1, "the accurate-math build runs the scalar flavours only");
   float inf, rate;
   br_inf_rate_exact<1>(v, inf, rate); s[1] = rush_larsen_rate(s[1], inf, rate, neg_dt);
   br_inf_rate_exact<2>(v, inf, rate); s[2] = rush_larsen_rate(s[2], inf, rate, neg_dt);
@@ -109,84 +113,78 @@ __device__ __forceinline__ void br_gates_exact(float v, float rk, float (&s)[7],
   (void)rk;
 #else
   // m: a = -(v+47)/expm1(-0.1(v+47)), b = 40 e^{-0.056(v+72)}
-  const float zm = -0.1f * (v + 47.f);
-  const float E10 = m_exp(zm);
+  const T v47 = v + T(47.f);
+  const T zm = T(-0.1f) * v47;
+  const T E10 = m_exp(zm);
   {
-    float q = 1.38888888888889e-3f;                // m_expm1(zm) with its exponential kept
-    q = fmaf(q, zm, 8.33333333333333e-3f);
-    q = fmaf(q, zm, 4.16666666666667e-2f);
-    q = fmaf(q, zm, 1.66666666666667e-1f);
-    q = fmaf(q, zm, 0.5f);
-    q = fmaf(q * zm, zm, zm);
-    const float den = fabsf(zm) < 0.125f ? q : E10 - 1.0f;
-    const float a = m_div(-1.f * (v + 47.f), den);
-    const float b = m_exp_affine(-0.056f * (v + 72.f), 40.f, 0.f);
-    const float rate = a + b;
+    const T den = sel(lt(vabs(zm), T(0.125f)), expm1_poly(zm), E10 - T(1.0f));   // m_expm1 with its exponential kept
+    const T a = m_div(-v47, den);
+    const T b = m_exp_affine(T(-0.056f) * (v + T(72.f)), 40.f, 0.f);
+    const T rate = a + b;
     s[1] = rush_larsen_rate(s[1], m_div(a, rate), rate, neg_dt);
   }
   // h: a = 0.126 e^{-0.25(v+77)}, b = 1.7/(e^{-0.082(v+22.5)} + 1)
-  const float E25 = m_exp(-.25f * (v + 77.f));
+  const T E25 = m_exp(T(-.25f) * (v + T(77.f)));
   {
-    const float a = 0.126f * E25;
-    const float b = m_div(1.7f, m_exp_affine(-0.082f * (v + 22.5f), 1.f, 1.f));
-    const float rate = a + b;
+    const T a = T(0.126f) * E25;
+    const T b = m_div(1.7f, m_exp_affine(T(-0.082f) * (v + T(22.5f)), 1.f, 1.f));
+    const T rate = a + b;
     s[2] = rush_larsen_rate(s[2], m_div(a, rate), rate, neg_dt);
   }
   if (SLOW) {
     // j: a = 0.055 e^{-0.25(v+78)}/(e^{-0.2(v+78)} + 1), b = 0.3/(e^{-0.1(v+32)} + 1)
-    const float E20 = m_exp(-0.2f * (v + 78.f));
-    s[3] = rush_larsen_frac(s[3], E25 * (0.055f * 0.7788007830714049f), E20 + 1.f, 0.3f,
-                            fmaf(E10, 4.4816890703380645f, 1.f), neg_dt_slow);
+    const T E20 = m_exp(T(-0.2f) * (v + T(78.f)));
+    s[3] = rush_larsen_frac(s[3], E25 * T(0.055f * 0.7788007830714049f), E20 + T(1.f), T(0.3f),
+                            vfma(E10, T(4.4816890703380645f), T(1.f)), neg_dt_slow);
     // d (rates doubled, br.py:46-48): a = 0.19 e^{-0.01(v-5)}/(e^{-0.072(v-5)} + 1),
     //                                 b = 0.14 e^{-0.017(v+44)}/(e^{0.05(v+44)} + 1)
-    s[4] = rush_larsen_frac(s[4], m_exp_affine(-0.01f * (v - 5.f), (float)(2 * 0.095), 0.f),
-                            m_exp_affine(-0.072f * (v - 5.f), 1.f, 1.f),
-                            m_exp_affine(-0.017f * (v + 44.f), (float)(2 * 0.07), 0.f),
-                            m_exp_affine(0.05f * (v + 44.f), 1.f, 1.f), neg_dt_slow);
+    const T v5 = v - T(5.f), v44 = v + T(44.f), v28 = v + T(28.f), v50 = v + T(50.f);
+    s[4] = rush_larsen_frac(s[4], m_exp_affine(T(-0.01f) * v5, (float)(2 * 0.095), 0.f),
+                            m_exp_affine(T(-0.072f) * v5, 1.f, 1.f),
+                            m_exp_affine(T(-0.017f) * v44, (float)(2 * 0.07), 0.f),
+                            m_exp_affine(T(0.05f) * v44, 1.f, 1.f), neg_dt_slow);
     // f (doubled): a = 0.024 e^{-0.008(v+28)}/(e^{0.15(v+28)} + 1),
     //              b = 0.013 e^{-0.02(v+30)}/(e^{-0.2(v+30)} + 1)
-    s[5] = rush_larsen_frac(s[5], m_exp_affine(-0.008f * (v + 28.f), (float)(2 * 0.012), 0.f),
-                            m_exp_affine(0.15f * (v + 28.f), 1.f, 1.f),
-                            m_exp_affine(-0.02f * (v + 30.f), (float)(2 * 0.0065), 0.f),
-                            fmaf(E20, 14764.781565577266f, 1.f), neg_dt_slow);
+    s[5] = rush_larsen_frac(s[5], m_exp_affine(T(-0.008f) * v28, (float)(2 * 0.012), 0.f),
+                            m_exp_affine(T(0.15f) * v28, 1.f, 1.f),
+                            m_exp_affine(T(-0.02f) * (v + T(30.f)), (float)(2 * 0.0065), 0.f),
+                            vfma(E20, T(14764.781565577266f), T(1.f)), neg_dt_slow);
     // xi: a = 0.0005 e^{0.083(v+50)}/(e^{0.057(v+50)} + 1), b = 0.0013 e^{-0.06(v+20)}/(e^{-0.04(v+20)} + 1)
-    s[6] = rush_larsen_frac(s[6], m_exp_affine(0.083f * (v + 50.f), 0.0005f, 0.f),
-                            m_exp_affine(0.057f * (v + 50.f), 1.f, 1.f),
-                            m_exp_affine(-0.06f * (v + 20.f), 0.0013f, 0.f),
-                            fmaf(rk, 0.44932896411722156f, 1.f), neg_dt_slow);
+    s[6] = rush_larsen_frac(s[6], m_exp_affine(T(0.083f) * v50, 0.0005f, 0.f),
+                            m_exp_affine(T(0.057f) * v50, 1.f, 1.f),
+                            m_exp_affine(T(-0.06f) * (v + T(20.f)), 0.0013f, 0.f),
+                            vfma(rk, T(0.44932896411722156f), T(1.f)), neg_dt_slow);
   }
 #endif
 }
 // rush_larsen with the argument-compensated expm1 (same result class, three instructions longer)
-__device__ __forceinline__ float rush_larsen_comp(float g, float g_inf, float tau, float neg_dt) {
-  float e = m_expm1(m_div(neg_dt, tau));
-  return clip_tf(fmaf(g - g_inf, e, g), 0.00001f, 0.99999f);
+template <class T> __device__ __forceinline__ T rush_larsen_comp(T g, T g_inf, T tau, float neg_dt) {
+  const T e = m_expm1(m_div(T(neg_dt), tau));
+  return clip_tf(vfma(g - g_inf, e, g), 0.00001f, 0.99999f);
 }
-// Horner evaluation of c0 + c1 x + ... + c8 x^8.  Every FMA has exactly ONE constant-bank operand
-// (the coefficient lives in the kernel parameter bank), so no LDC is needed; Estrin's scheme was
-// measured slower because its two-constant FMAs saturate the ADU pipe with constant loads.  The
-// 12 gate functions are independent chains, which is all the ILP the scheduler needs.
-__device__ __forceinline__ float br_poly8(const float* __restrict__ c, float x) {
-  float r = c[8];
+// Horner evaluation of c0 + c1 x + ... + c8 x^8.  Every FMA takes its coefficient straight from the
+// kernel parameter bank (scalar: a constant-bank operand; packed: a uniform register broadcast to
+// both lanes), so no per-thread register holds a coefficient; Estrin's scheme was measured slower
+// because its two-constant FMAs saturate the ADU pipe with constant loads.  The 12 gate functions
+// are independent chains, which is all the ILP the scheduler needs.
+template <class T> __device__ __forceinline__ T br_poly8(const float* __restrict__ c, T x) {
+  T r = T(c[8]);
 #pragma unroll
-  for (int i = 7; i >= 0; --i) r = fmaf(r, x, c[i]);
+  for (int i = 7; i >= 0; --i) r = vfma(r, x, T(c[i]));
   return r;
 }
 
 // strict-order evaluation of the reference's polynomial gates (br.py:215, 289-301, 327-331): x by an
 // fp32 DIVISION, S_i = (2x) S_{i-1}, r = d_0 + d_1 S_1 + ... left to right with one rounding per
 // multiply and per add (no FMA), then ionic.py:115-123 with IEEE division, libm expm1f and unfused
-// multiply / add.  d = the fp32-rounded table coefficients, unscaled.  This is the reference's own
-// operation sequence; the only thing left to differ is the last bit of expm1f (CUDA libm vs glibc).
-__device__ __forceinline__ float br_strict_eval(const float* __restrict__ d, const float (&S)[9]) {
-  float r = __fadd_rn(d[0], __fmul_rn(d[1], S[1]));
+// multiply / add (rush_larsen_strict).  d = the fp32-rounded table coefficients, unscaled.  This is
+// the reference's own operation sequence; the only thing left to differ is the last bit of expm1f
+// (CUDA libm vs glibc).
+template <class T> __device__ __forceinline__ T br_strict_eval(const float* __restrict__ d, const T (&S)[9]) {
+  T r = add_rn(T(d[0]), mul_rn(T(d[1]), S[1]));
 #pragma unroll
-  for (int i = 2; i <= 8; ++i) r = __fadd_rn(r, __fmul_rn(d[i], S[i]));
+  for (int i = 2; i <= 8; ++i) r = add_rn(r, mul_rn(T(d[i]), S[i]));
   return r;
-}
-__device__ __forceinline__ float rush_larsen_strict(float g, float g_inf, float tau, float neg_dt) {
-  const float e = expm1f(__fdiv_rn(neg_dt, tau));
-  return clip_tf(__fadd_rn(g, __fmul_rn(__fsub_rn(g, g_inf), e)), 0.00001f, 0.99999f);
 }
 
 // CHEBY: 0 = exact gates (br.py:175-205), 1 = polynomial gates by Horner's scheme (default for
@@ -197,6 +195,7 @@ struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
   static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
   static constexpr int VEC_SMALL = 1;   // cells per thread on small grids (kSmallGridCells)
+  static constexpr bool PACKED = !FIB_ACCURATE_MATH;   // two cells per thread run as one f2 pair
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)
@@ -228,22 +227,23 @@ struct BeelerReuter {
   };
   static __device__ __forceinline__ void prologue(const StepArgs<BeelerReuter>&) {}
 
-  static __device__ __forceinline__ void cell(const StepArgs<BeelerReuter>& a, float /*raw*/,
-                                              float V0, float lap, float (&s)[NS], float& Vnew) {
+  template <class T>
+  static __device__ __forceinline__ void cell(const StepArgs<BeelerReuter>& a, T /*raw*/, T V0, T lap,
+                                              T (&s)[NS], T& Vnew) {
     const Params& p = a.p;
-    const float C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
+    const T C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
     // every current exponential is k = e^{0.04 V0} times a constant; the exact gates reuse 1/k.
     // (The polynomial flavour computes k AFTER its gates: hoisting it costs that kernel 10 %.)
-    float k, rk;
+    T k, rk;
 
     if (CHEBY == 2) {
-      const float x = __fdiv_rn(__fsub_rn(V0, -30.0f), 60.0f);      // br.py:215
-      const float tx = __fmul_rn(2.0f, x);                          // br.py:299: T = 2*x*Ts[-1]
-      float S[9];
-      S[0] = 1.0f;
+      const T x = div_rn(sub_rn(V0, T(-30.0f)), T(60.0f));          // br.py:215
+      const T tx = mul_rn(T(2.0f), x);                              // br.py:299: T = 2*x*Ts[-1]
+      T S[9];
+      S[0] = T(1.0f);
       S[1] = x;
 #pragma unroll
-      for (int i = 2; i <= 8; ++i) S[i] = __fmul_rn(tx, S[i - 1]);
+      for (int i = 2; i <= 8; ++i) S[i] = mul_rn(tx, S[i - 1]);
 #define FIB_BR_GATE(g, idx, ndt)                                                            \
   s[idx] = rush_larsen_strict(s[idx], br_strict_eval(p.poly[2 * (g)], S),                  \
                               br_strict_eval(p.poly[2 * (g) + 1], S), ndt)
@@ -256,11 +256,11 @@ struct BeelerReuter {
         FIB_BR_GATE(5, 5, p.neg_dt_slow);                          // f
       }
 #undef FIB_BR_GATE
-      k = m_exp(0.04f * V0);
+      k = m_exp(T(0.04f) * V0);
       rk = m_rcp(k);
     } else if (CHEBY == 1) {
       // x = (V0 - 0.5(max+min)) / (0.5(max-min)) = (V0 + 30)/60   (br.py:215)
-      const float x = (V0 + 30.0f) * (1.0f / 60.0f);
+      const T x = (V0 + T(30.0f)) * T(1.0f / 60.0f);
 #define FIB_BR_GATE(RL, g, idx, ndt) \
   s[idx] = RL(s[idx], br_poly8(p.poly[2 * (g)], x), br_poly8(p.poly[2 * (g) + 1], x), ndt)
       if (SLOW) {
@@ -277,10 +277,10 @@ struct BeelerReuter {
         FIB_BR_GATE(rush_larsen, 5, 5, p.neg_dt_slow);         // f
       }
 #undef FIB_BR_GATE
-      k = m_exp(0.04f * V0);
+      k = m_exp(T(0.04f) * V0);
       rk = m_rcp(k);
     } else {
-      k = m_exp(0.04f * V0);
+      k = m_exp(T(0.04f) * V0);
       rk = m_rcp(k);
       br_gates_exact<SLOW>(V0, rk, s, p.neg_dt, p.neg_dt_slow);
     }
@@ -290,39 +290,30 @@ struct BeelerReuter {
     constexpr float E53 = 8.331137487687693f;     // e^{0.04*53}
     constexpr float E77 = 21.75840239619708f;    // e^{0.04*77}
     constexpr float E35 = 4.055199966844675f;    // e^{0.04*35}
-    const float k53 = k * E53;
-    const float d23 = V0 + 23.0f;
+    const T k53 = k * T(E53);
+    const T d23 = V0 + T(23.0f);
     // (V0+23) / (1 - e^{-0.04 (V0+23)}): removable singularity at -23 mV.  Away from it
     // 1 - e^{-0.92}/k is accurate and free (k is already known); within +-3 mV the expm1
-    // polynomial takes over.
+    // polynomial takes over (|z| < 0.125 <=> within 3.1 mV of the singularity).
     constexpr float E23N = 0.3985190410845142f;   // e^{-0.04*23}
-    float one_m_e = fmaf(-E23N, rk, 1.0f);
-    {
-      const float z = -0.04f * d23;               // |z| < 0.125 <=> within 3.1 mV of the singularity
-      float q = 1.38888888888889e-3f;
-      q = fmaf(q, z, 8.33333333333333e-3f);
-      q = fmaf(q, z, 4.16666666666667e-2f);
-      q = fmaf(q, z, 1.66666666666667e-1f);
-      q = fmaf(q, z, 0.5f);
-      q = fmaf(q * z, z, z);                      // expm1(z)
-      one_m_e = fabsf(z) < 0.125f ? -q : one_m_e;
-    }
-    const float sing = m_div(d23, one_m_e);
-    const float iK1 = 0.35f * (m_div(4.f * fmaf(k, E85, -1.f), fmaf(k53, k53, k53)) + 0.2f * sing);
-        // measured: reusing 1/k is +3 % for the six-gate polynomial step, -1.5 % for its two-gate one
-    const float ix1 = (SLOW || CHEBY != 1)
-                          ? XI * 0.8f * (fmaf(k, E77, -1.f) * (rk * (1.0f / E35)))
-                          : XI * 0.8f * m_div(fmaf(k, E77, -1.f), k * E35);
-    const float iNa = (4.0f * M * M * M * H * J + 0.005f) * (V0 - 50.0f);
-    const float ECa = -82.3f - 13.0278f * m_log(C);
-    const float iCa = 0.09f * D * F * (V0 - ECa);
-    const float I_sum = iK1 + ix1 + iNa + iCa;
+    const T z = T(-0.04f) * d23;
+    const T one_m_e = sel(lt(vabs(z), T(0.125f)), -expm1_poly(z), vfma(T(-E23N), rk, T(1.0f)));
+    const T sing = m_div(d23, one_m_e);
+    const T iK1 = T(0.35f) * vfma(T(0.2f), sing,
+                                  m_div(T(4.f) * vfma(k, T(E85), T(-1.f)), vfma(k53, k53, k53)));
+    // measured: reusing 1/k is +3 % for the six-gate polynomial step, -1.5 % for its two-gate one
+    const T ix1 = (SLOW || CHEBY != 1)
+                      ? XI * T(0.8f) * (vfma(k, T(E77), T(-1.f)) * (rk * T(1.0f / E35)))
+                      : XI * T(0.8f) * m_div(vfma(k, T(E77), T(-1.f)), k * T(E35));
+    const T gNa = vfma(T(4.0f) * M * M * M * H, J, T(0.005f));       // g_Na M^3 H J + g_NaC
+    const T ECa = vfma(T(-13.0278f), m_log(C), T(-82.3f));
+    const T iCa = T(0.09f) * D * F * (V0 - ECa);
+    const T I_sum = vfma(gNa, V0 - T(50.0f), (iK1 + ix1) + iCa);
     // (V0 + ddt*lap) - dt*I_sum/C_m with the reference's rounding sequence (br.py:167-168): the
     // result crosses 0 mV while the operands are ~80 mV, so no FMA contraction here
-    Vnew = clip_tf(__fsub_rn(__fadd_rn(V0, __fmul_rn(p.ddt, lap)), __fmul_rn(p.dt, I_sum)), -85.0f,
-                    25.0f);
-    const float dC = -1.0e-7f * iCa + 0.07f * (1.0e-7f - C);
-    s[0] = fmaf(p.dt, dC, C);
+    Vnew = clip_tf(sub_rn(add_rn(V0, mul_rn(T(p.ddt), lap)), mul_rn(T(p.dt), I_sum)), -85.0f, 25.0f);
+    const T dC = vfma(T(-1.0e-7f), iCa, T(0.07f) * (T(1.0e-7f) - C));
+    s[0] = vfma(T(p.dt), dC, C);
   }
 };
 

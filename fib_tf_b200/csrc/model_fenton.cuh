@@ -18,6 +18,7 @@ struct Fenton4v {
   static constexpr int AUTO_R = 4;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS = FIB_4V_MINB;
   static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
+  static constexpr bool PACKED = false;   // HBM-bound already: scalar cells, four per thread
   static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
   static constexpr bool NEED_LAP = true;
