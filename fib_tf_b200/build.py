@@ -6,7 +6,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'fib_capi.cu')
 OUT = os.path.join(HERE, 'libfibb200.so')
-NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+# -fmad=false: multiply-adds are fused only where the source says so (fmaf / vfma / fma.rn.f32x2).  That
+# makes every kernel that shares a cell function -- one step per launch, two steps per launch, the
+# persistent on-chip kernel, the scalar and the packed (f32x2) flavours -- round identically, so they can
+# be (and are) tested BIT-identical to each other; left to the compiler, contraction differs per kernel.
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
               '-Xcompiler', '-fPIC', '-shared']
 
 

@@ -16,6 +16,7 @@
 #include "model_court.cuh"
 #include "model_fenton.cuh"
 #include "fib_fused.cuh"
+#include "fib_persist.cuh"
 
 using namespace fib;
 
@@ -136,6 +137,13 @@ struct fib_ctx {
   unsigned long long ring_fetched = 0;
   int watch_var = -1, watch_row = -1, watch_col = -1;
   float* weights[4] = {nullptr, nullptr, nullptr, nullptr};   // user masks, halo layout like phase
+  // persistent on-chip kernel (fib_persist.cuh): small unsharded 4v / BR grids
+  int persist = -1;                   // -1 not decided yet, 0 no, 1 yes
+  int persist_th = 0, persist_tiles = 0, persist_bw = 0;
+  unsigned* pflags = nullptr;         // [tiles] steps published, monotonic
+  unsigned pbase = 0;
+  int* perr = nullptr;                // page-locked, device-visible: raised by a timed-out neighbour wait
+  CUtensorMap pmap_x[2], pmap_s[8];
   // NCCL
   void* comm = nullptr;
   int nranks = 1, rank = 0;
@@ -145,6 +153,8 @@ struct fib_ctx {
   bool top_is_border() const { return g.row0 == 0; }
   bool bottom_is_border() const { return g.row0 + g.rows == g.H; }
 };
+
+static int check_persist_error(fib_ctx* c);
 
 struct DevGuard {
   int prev = -1;
@@ -491,6 +501,8 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->red);
   cudaFree(c->ring);
   cudaFree(c->ring_count);
+  cudaFree(c->pflags);
+  if (c->perr) cudaFreeHost(c->perr);
   for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
   for (cudaEvent_t e : {c->ev_start, c->ev_stop, c->ev_bnd, c->ev_comm, c->ev_group})
     if (e) cudaEventDestroy(e);
@@ -570,7 +582,7 @@ extern "C" int fib_get_state(fib_ctx* c, int var, float* host, size_t n) {
   CU(cudaMemcpy2DAsync(host, c->g.W * sizeof(float), owned_rows(c, var), c->g.pitch * sizeof(float),
                        c->g.W * sizeof(float), c->g.rows, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_persist_error(c);
 }
 
 extern "C" int fib_get_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1, float* host) {
@@ -955,6 +967,186 @@ static int nccl_exchange(fib_ctx* c, int b, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// the persistent on-chip kernel (fib_persist.cuh): eligibility, tensor maps, launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// fp32 plane [rows][W] with row pitch `pitch` floats, box {bw, bh}
+static bool make_tile_map(CUtensorMap* m, float* base, int W, int rows, int pitch, int bw, int bh) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+template <class MS, class MF, int TH, bool PHASE>
+static cudaError_t launch_persist_t(fib_ctx* c, const PersistArgs<MS, MF>& a) {
+  PersistMaps<MS::NS> maps;
+  maps.x[0] = c->pmap_x[0];
+  maps.x[1] = c->pmap_x[1];
+  for (int k = 0; k < MS::NS; ++k) maps.s[k] = c->pmap_s[k];
+  auto kern = persist_kernel<MS, MF, TH, PHASE>;
+  constexpr size_t smem = persist_smem_bytes<MS::NS, TH>();
+  static bool attr_set = false;           // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(c->persist_tiles);
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;       // all tiles co-resident, or the launch fails
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  snprintf(last_kernel_name(), 160, "persist_kernel<%s,TH=%d,PHASE=%d>", MS::name(), TH, PHASE ? 1 : 0);
+  return cudaLaunchKernelEx(&cfg, kern, maps, c->g, a);
+}
+
+template <class MS, class MF>
+static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_th) {
+  a.x[0] = c->x[0];
+  a.x[1] = c->x[1];
+  a.cur = c->cur;
+  a.nsteps = c->dt_per_step;
+  a.flags = c->pflags;
+  a.base = c->pbase;
+  a.err = c->perr;
+  a.phase = c->phase;
+  a.pmask = c->pmask;
+  a.pmask_pitch = c->pmask_pitch;
+  a.bw = c->persist_bw;
+  const bool ph = c->phase != nullptr;
+  (void)max_th;
+  switch (c->persist_th) {
+    case 2: return ph ? launch_persist_t<MS, MF, 2, true>(c, a) : launch_persist_t<MS, MF, 2, false>(c, a);
+    case 4: return ph ? launch_persist_t<MS, MF, 4, true>(c, a) : launch_persist_t<MS, MF, 4, false>(c, a);
+    case 8:
+      if constexpr (MS::NS <= 3)
+        return ph ? launch_persist_t<MS, MF, 8, true>(c, a) : launch_persist_t<MS, MF, 8, false>(c, a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Decides once per context (and again after fib_set_phase) whether ODE iterations run as the persistent
+// kernel: Fenton 4v (one step per launch layout) or Beeler-Reuter, unsharded, W <= 512, at most 8 (4v) /
+// 4 (BR) rows per SM, cooperative launch available.  FIB_PERSIST=0 or FIB_F_NO_PERSIST switch it off.
+static void decide_persist(fib_ctx* c) {
+  c->persist = 0;
+  static const bool env_on = !(getenv("FIB_PERSIST") && atoi(getenv("FIB_PERSIST")) == 0);
+  if (!env_on || (c->cfg.flags & FIB_F_NO_PERSIST)) return;
+  const int model = c->cfg.model;
+  if (!(model == FIB_FENTON4V || model == FIB_BR) || c->fuse != 1) return;
+  if (c->comm || c->g.rows != c->g.H || c->g.W > kPersistThreads) return;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device) != cudaSuccess || !coop) return;
+  const int max_th = model == FIB_FENTON4V ? 8 : 4;
+  const int need = (c->g.H + c->sms - 1) / c->sms;
+  int th = 2;
+  while (th < need) th *= 2;
+  if (th > max_th) return;
+  const int bw = c->g.W >= kPersistBox ? kPersistBox : (c->g.W + 3) / 4 * 4;
+  const int P = c->g.pitch;
+  bool ok = make_tile_map(&c->pmap_x[0], c->x[0] + P, c->g.W, c->g.H, P, bw, 1) &&
+            make_tile_map(&c->pmap_x[1], c->x[1] + P, c->g.W, c->g.H, P, bw, 1);
+  for (int k = 0; ok && k + 1 < c->nvars; ++k) ok = make_tile_map(&c->pmap_s[k], c->s[k], c->g.W, c->g.H, P, bw, th);
+  if (!ok) return;
+  const int tiles = (c->g.H + th - 1) / th;
+  if (!c->pflags) {
+    if (cudaMalloc(&c->pflags, sizeof(unsigned) * (size_t)c->sms * 2) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemsetAsync(c->pflags, 0, sizeof(unsigned) * (size_t)c->sms * 2, c->stream);
+    if (cudaHostAlloc(&c->perr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
+    *c->perr = 0;
+  }
+  c->persist_th = th;
+  c->persist_tiles = tiles;
+  c->persist_bw = bw;
+  c->persist = 1;
+}
+
+// one ODE iteration (dt_per_step time steps) as ONE launch
+static int run_iteration_persist(fib_ctx* c) {
+  const double dt = c->cfg.dt;
+  const uint32_t fl = c->cfg.flags;
+  cudaError_t e;
+  if (c->cfg.model == FIB_FENTON4V) {
+    PersistArgs<Fenton4v, Fenton4v> a;
+    for (int i = 0; i < kPersistMaxSteps; ++i) a.slow[i] = 1;
+    a.ps.dt = a.pf.dt = (float)dt;
+    a.ps.ddt = a.pf.ddt = (float)(c->cfg.diff * dt);
+    e = launch_persist_m<Fenton4v, Fenton4v>(c, a, 8);
+  } else {
+    const bool cheby = fl & FIB_F_CHEBY, strict = cheby && (fl & FIB_F_CHEBY_STRICT), skip = fl & FIB_F_SKIP;
+    if (cheby && !c->have_cheb) return fail(FIB_E_STATE, "cheby=True but FIB_TABLE_BR_CHEBY has not been set");
+    auto go = [&](auto ts, auto tf) {
+      using MS = decltype(ts);
+      using MF = decltype(tf);
+      PersistArgs<MS, MF> a;
+      for (int i = 0; i < kPersistMaxSteps; ++i) a.slow[i] = skip ? (i == 0) : 1;     // br.py:96-107
+      auto fill = [&](auto& p, int n) {
+        p.dt = (float)dt;
+        p.neg_dt = (float)(-dt);
+        p.neg_dt_slow = (float)(-(dt * n));
+        p.ddt = (float)(c->cfg.diff * dt);
+        for (int g = 0; g < 12; ++g)
+          for (int i = 0; i < 9; ++i)
+            p.poly[g][i] = (i < 2 || strict) ? c->cheb[g][i] : ldexpf(c->cheb[g][i], i - 1);
+      };
+      fill(a.ps, skip ? 5 : 1);
+      fill(a.pf, 0);
+      return launch_persist_m<MS, MF>(c, a, 4);
+    };
+    if (strict)     e = go(BeelerReuter<2, true>(), BeelerReuter<2, false>());
+    else if (cheby) e = go(BeelerReuter<1, true>(), BeelerReuter<1, false>());
+    else            e = go(BeelerReuter<0, true>(), BeelerReuter<0, false>());
+  }
+  if (e != cudaSuccess) {
+    // e.g. the tiles cannot all be resident (another context holds SMs): never a partial launch.
+    // Fall back to one launch per step for the rest of this context's life.
+    cudaGetLastError();
+    c->persist = 0;
+    return 1;           // caller retries on the plain path
+  }
+  c->launches++;
+  c->pbase += (unsigned)c->dt_per_step;
+  if (c->dt_per_step & 1) c->cur ^= 1;
+  return 0;
+}
+
+static int check_persist_error(fib_ctx* c) {
+  if (c->perr && *c->perr) {
+    *c->perr = 0;
+    return fail(FIB_E_STATE, "persistent kernel: a tile waited for its neighbour beyond the spin limit "
+                "(state is invalid); set FIB_PERSIST=0 to use one launch per step");
+  }
+  return 0;
+}
+
 // fib_probe_watch: after an ODE iteration, append the watched cell of the CURRENT buffers to the ring
 static int record_probe(fib_ctx* c, int op) {
   if (c->watch_var < 0 || op != FIB_OP_ODE) return 0;
@@ -1036,6 +1228,18 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
   }
   if (c->g.rows != c->g.H)
     return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
+  if (c->persist < 0) decide_persist(c);
+  if (c->persist == 1 && op == FIB_OP_ODE) {
+    int i = 0;
+    for (; i < n_iter; ++i) {
+      int r = run_iteration_persist(c);
+      if (r > 0) break;                 // could not launch: plain path from here on
+      if (r) return r;
+      if ((r = record_probe(c, op))) return r;
+    }
+    if (i == n_iter) return 0;
+    n_iter -= i;
+  }
   if (c->cfg.flags & FIB_F_NO_GRAPH) {
     for (int i = 0; i < n_iter; ++i) {
       int r = run_iteration_plain(c, op);
@@ -1429,7 +1633,7 @@ extern "C" int fib_sync(fib_ctx* c) {
   CU(cudaStreamSynchronize(c->comm_stream));
   CU(cudaStreamSynchronize(c->copy_stream));
   c->snap_pending = false;
-  return 0;
+  return check_persist_error(c);
 }
 extern "C" int fib_timer_start(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
@@ -1490,5 +1694,6 @@ extern "C" int fib_comm_init(fib_ctx* c, int nranks, int rank, const void* id128
   c->nranks = nranks;
   c->rank = rank;
   c->halo_dirty = true;
+  c->persist = 0;          // the persistent kernel is for unsharded grids
   return 0;
 }

@@ -1,0 +1,304 @@
+// fib_persist.cuh -- the persistent on-chip kernel for the latency regime (the reference's own
+// 512 x 512 configurations, BASELINE configs 1 and 2): ONE launch advances a whole run() iteration
+// (10 time steps of 4v, 5 of Beeler-Reuter; fenton.py:133-138, br.py:96-107) with the state resident
+// on chip between the steps.
+//
+// Why: a 512^2 state is 4-8 MiB.  One step per launch leaves such a grid launch-latency bound (3.1 us
+// per 4v step against 1.3 us of HBM time and ~0.7 us of issue time, profiles/r1_suite.json); k-step
+// temporal blocking by halo recomputation would double the arithmetic at this tile size.  Here
+// nothing is recomputed and nothing goes through HBM between steps:
+//
+//   * the grid is cut into row tiles of TH rows x W columns (W <= 512), one tile per CTA, one CTA per SM
+//     (cooperative launch: all CTAs are co-resident by construction);
+//   * TMA 2-D tile loads (cp.async.bulk.tensor, mbarrier completion) bring the tile into shared memory at
+//     the start; the non-diffusing planes then live in REGISTERS (a thread owns one column of its tile)
+//     and the diffusing variable in a double-buffered shared-memory tile; TMA tile stores write
+//     everything back once at the end;
+//   * per step only the two edge rows of the diffusing variable leave the SM: each CTA stores them
+//     into the global plane (L2) and release-stores a step counter; its two neighbours acquire-poll
+//     that counter and read the rows back with L2 loads.  A step first advances the interior rows,
+//     which need nothing from outside, and only then the edge rows, so the neighbour hand-shake is
+//     hidden behind arithmetic.  One __syncthreads per step.
+//
+// Every cell goes through the SAME cell function and the same Laplacian / phase-term code as
+// step_kernel (fib_kernels.cuh), with the same clamped index map, and the library is built with
+// -fmad=false, so the result is BIT-IDENTICAL to one launch per step (tests/test_gpu_persist.py).
+//
+// Deadlock safety: inter-CTA waits exist only under a cooperative launch (fib_capi.cu refuses the
+// path otherwise); every spin loop is bounded (kSpinLimit polls, ~1 s) and raises *err instead of
+// hanging the device.
+#pragma once
+#include <cuda.h>
+
+#include "model_br.cuh"
+#include "model_fenton.cuh"
+
+namespace fib {
+
+constexpr int kPersistThreads = 512;      // one thread per column: W <= 512
+constexpr int kPersistBox = 256;          // TMA box width (elements; the hardware limit per dimension)
+constexpr int kPersistWP = 512 + 64;      // padded row of the diffusing tile: data at +32 floats (128 B)
+constexpr unsigned kSpinLimit = 1u << 22;
+
+// ---- PTX wrappers: mbarrier + TMA (SASS: SYNCS / UTMALDG / UTMASTG) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 2-D tile load global -> shared, completion counted in bytes on `bar`; (x, y) = (column, row)
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+// 2-D tile store shared -> global (rows / columns outside the tensor are clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src_smem)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- arguments --------------------------------------------------------------------------------
+constexpr int kPersistMaxSteps = 10;
+
+template <int NS>
+struct PersistMaps {
+  CUtensorMap x[2];     // the diffusing variable's two buffers, owned rows, box {256, 1}
+  CUtensorMap s[NS];    // the other planes, box {256, TH}
+};
+
+template <class MS, class MF>
+struct PersistArgs {
+  float* x[2];                 // the same two buffers as plain pointers (halo layout: row g at (g + 1) * pitch)
+  int cur;                     // x[cur] holds the state at the start of the launch
+  int nsteps;                  // time steps of this launch (dt_per_step)
+  unsigned char slow[kPersistMaxSteps];   // per step: 1 -> MS (e.g. BR n > 0), 0 -> MF (BR n == 0)
+  unsigned* flags;             // [tiles] steps published so far (monotonic over the whole run)
+  unsigned base;               // value of every flag at the start of this launch
+  int* err;                    // set to 1 if a neighbour wait ran into the spin limit
+  const float* phase;          // halo layout (one row), or nullptr
+  const unsigned char* pmask;  // [rows][pmask_pitch] as in StepArgs
+  int pmask_pitch;
+  int bw;                      // TMA box width actually encoded (min(256, W rounded up to 4))
+  typename MS::Params ps;      // parameters of the MS steps
+  typename MF::Params pf;      // parameters of the MF steps
+};
+
+// ---- the kernel ----------------------------------------------------------------------------------
+// MS / MF: the cell types of the "slow" and "fast" steps of a schedule (Fenton4v twice; BeelerReuter<C,true>
+// and <C,false> for br.py's skip schedule).  TH: rows per tile.  PHASE: phase field present.
+template <class MS, class MF, int TH, bool PHASE>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, const PersistArgs<MS, MF> a) {
+  constexpr int NS = MS::NS;
+  static_assert(MS::NS == MF::NS, "slow / fast steps share the state layout");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ub = reinterpret_cast<float*>(smem_raw);                         // [2][TH + 2][kPersistWP]
+  float* st = ub + 2 * (TH + 2) * kPersistWP;                             // [NS][2 column blocks][TH rows of bw][.. 256]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(st + NS * TH * 512);
+
+  const int t = threadIdx.x, tile = blockIdx.x, ntiles = gridDim.x;
+  const int W = g.W, H = g.H, pitch = g.pitch;
+  const int r0 = tile * TH;
+  const int nrows = min(TH, H - r0);
+  const int c = t;
+  const bool active = c < W;
+  const int nblk = (W + kPersistBox - 1) / kPersistBox;
+  auto urow = [&](int p, int li) { return ub + (p * (TH + 2) + li) * kPersistWP + 32; };   // column 0 of local row li
+
+  // ---- TMA in: the diffusing tile row by row into the padded buffer, the other planes as {bw, TH} boxes
+  if (t == 0) {
+    mbar_init(bar, 1);
+    fence_async_smem();
+  }
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(bar, (uint32_t)((TH + NS * TH) * nblk * a.bw * sizeof(float)));
+    for (int b = 0; b < nblk; ++b) {
+      for (int i = 0; i < TH; ++i) tma_load_2d(urow(0, i + 1) + b * kPersistBox, &maps.x[a.cur], b * kPersistBox, r0 + i, bar);
+      for (int k = 0; k < NS; ++k) tma_load_2d(st + (k * 2 + b) * TH * kPersistBox, &maps.s[k], b * kPersistBox, r0, bar);
+    }
+  }
+  // meanwhile: which of my cells have a non-trivial phase term (same flags as step_kernel)
+  unsigned phbits = 0;
+  if (PHASE && active) {
+#pragma unroll
+    for (int i = 0; i < TH; ++i)
+      if (i < nrows && a.pmask[(r0 + i) * a.pmask_pitch + (c >> 5)]) phbits |= 1u << i;
+  }
+  const int ccl = clampi(c - 1, 1, W - 2), ccc = clampi(c, 1, W - 2), ccr = clampi(c + 1, 1, W - 2);
+  while (!mbar_try_wait(bar, 0)) {}
+
+  float s[NS][TH];
+  {
+    const int b = c / kPersistBox, cb = c - b * kPersistBox;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+      for (int i = 0; i < TH; ++i) s[k][i] = active ? st[(k * 2 + b) * TH * kPersistBox + i * a.bw + cb] : 0.f;
+  }
+
+  StepArgs<MS> sa_s;
+  StepArgs<MF> sa_f;
+  sa_s.p = a.ps;
+  sa_f.p = a.pf;
+
+  // one cell: exactly step_kernel's arithmetic.  nN / nC / nS: the clamped-column triples of the
+  // enforced rows above / at / below; raw: the un-enforced centre value.
+  auto advance = [&](bool slow, int i, const float (&nN)[3], const float (&nC)[3], const float (&nS)[3],
+                     float raw) -> float {
+    float lap = lap9(nN[1], nS[1], nC[0], nC[2], nN[0], nS[0], nN[2], nS[2], nC[1]);
+    if (PHASE && ((phbits >> i) & 1u)) {
+      const int gr = r0 + i;
+      const float* ph = a.phase;
+      const int rN = (reflecti(gr - 1, H) + 1) * pitch, rC = (gr + 1) * pitch, rS = (reflecti(gr + 1, H) + 1) * pitch;
+      const float pN = ph[rN + c], pS = ph[rS + c];
+      const float pW = ph[rC + clampi(reflecti(c - 1, W), 0, W - 1)], pE = ph[rC + clampi(reflecti(c + 1, W), 0, W - 1)];
+      lap = __fadd_rn(lap, phase_term(nN[1], nS[1], nC[0], nC[2], pN, pS, pW, pE, ph[rC + c]));
+    }
+    float sl[NS], xnew;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
+    if (slow) MS::cell(sa_s, raw, nC[1], lap, sl, xnew);
+    else MF::cell(sa_f, raw, nC[1], lap, sl, xnew);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
+    return xnew;
+  };
+
+  for (int step = 0; step < a.nsteps; ++step) {
+    const int p = step & 1;                                  // shared buffer holding the state at this step
+    const float* xg = a.x[(a.cur + step) & 1];               // global plane with the neighbours' edge rows of it
+    float* xg_next = a.x[(a.cur + step + 1) & 1];
+    const bool slow = a.slow[step] != 0;
+    const unsigned want = a.base + step;
+    // neighbour rows (the ring): global rows r0 - 1 and r0 + TH, columns c-1, c, c+1 (clamped)
+    float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
+    const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
+    auto ring_ready = [&]() {
+      return (!need_top || ld_acquire(a.flags + tile - 1) >= want) && (!need_bot || ld_acquire(a.flags + tile + 1) >= want);
+    };
+    auto ring_load = [&]() {
+      if (!active) return;
+      if (need_top) {
+        const float* q = xg + (size_t)(r0 - 1 + 1) * pitch;
+        rt[0] = __ldcg(q + ccl); rt[1] = __ldcg(q + ccc); rt[2] = __ldcg(q + ccr);
+      }
+      if (need_bot) {
+        const float* q = xg + (size_t)(r0 + TH + 1) * pitch;
+        rb[0] = __ldcg(q + ccl); rb[1] = __ldcg(q + ccc); rb[2] = __ldcg(q + ccr);
+      }
+    };
+    // at step 0 the rows are there already (written by the previous launch / the upload)
+    bool have_ring = step == 0 || ring_ready();
+    if (have_ring) ring_load();
+
+    // triple of enforced values of global row gr (already clamped by the caller) at my three columns
+    auto triple = [&](int gr, float (&v)[3]) {
+      const int li = gr - r0 + 1;
+      if (li == 0) { v[0] = rt[0]; v[1] = rt[1]; v[2] = rt[2]; }
+      else if (li == TH + 1) { v[0] = rb[0]; v[1] = rb[1]; v[2] = rb[2]; }
+      else {
+        const float* q = urow(p, li);
+        v[0] = q[ccl]; v[1] = q[ccc]; v[2] = q[ccr];
+      }
+    };
+    auto do_row = [&](int i) {
+      const int gr = r0 + i;
+      float nN[3], nC[3], nS[3];
+      triple(clampi(gr - 1, 1, H - 2), nN);
+      triple(clampi(gr, 1, H - 2), nC);
+      triple(clampi(gr + 1, 1, H - 2), nS);
+      const float xnew = advance(slow, i, nN, nC, nS, urow(p, i + 1)[c]);
+      urow(p ^ 1, i + 1)[c] = xnew;
+      return xnew;
+    };
+
+    // interior rows: need nothing from outside the tile
+    if (active) {
+#pragma unroll
+      for (int i = 1; i < TH - 1; ++i)
+        if (i < nrows) do_row(i);
+    }
+    if (!have_ring) {
+      unsigned spins = 0;
+      while (!ring_ready()) {
+        if (++spins > kSpinLimit) { *a.err = 1; break; }
+      }
+      ring_load();
+    }
+    // edge rows, published to the neighbours straight from registers
+    if (active) {
+      const float top = do_row(0);
+      if (need_top) xg_next[(size_t)(r0 + 1) * pitch + c] = top;
+      if (TH > 1 && TH - 1 < nrows) {
+        const float bot = do_row(TH - 1);
+        if (need_bot) xg_next[(size_t)(r0 + TH - 1 + 1) * pitch + c] = bot;
+      } else if (TH == 1 && need_bot) {
+        xg_next[(size_t)(r0 + 1) * pitch + c] = top;
+      }
+    }
+    __syncthreads();            // shared tile of the next step complete; all edge stores issued
+    if (t == 0) {
+      __threadfence();
+      st_release(a.flags + tile, want + 1);
+    }
+  }
+
+  // ---- TMA out: registers -> staging, then tile stores (rows beyond the grid are clipped)
+  if (active) {
+    const int b = c / kPersistBox, cb = c - b * kPersistBox;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+      for (int i = 0; i < TH; ++i) st[(k * 2 + b) * TH * kPersistBox + i * a.bw + cb] = s[k][i];
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (t == 0) {
+    const int pf = a.nsteps & 1;
+    const CUtensorMap* mx = &maps.x[(a.cur + a.nsteps) & 1];
+    for (int b = 0; b < nblk; ++b) {
+      for (int i = 0; i < TH; ++i) tma_store_2d(mx, b * kPersistBox, r0 + i, urow(pf, i + 1) + b * kPersistBox);
+      for (int k = 0; k < NS; ++k)
+        if (MS::stores(k) || MF::stores(k)) tma_store_2d(&maps.s[k], b * kPersistBox, r0, st + (k * 2 + b) * TH * kPersistBox);
+    }
+    tma_store_commit_wait();
+  }
+}
+
+template <int NS, int TH>
+constexpr size_t persist_smem_bytes() {
+  return (size_t)(2 * (TH + 2) * kPersistWP + NS * TH * 512) * sizeof(float) + 64;
+}
+
+}  // namespace fib

@@ -34,6 +34,12 @@
 #ifndef FIB_BR_MINB_FAST
 #define FIB_BR_MINB_FAST 8
 #endif
+#ifndef FIB_BR_PACKED            /* two cells per thread as one f2 pair; 0 = two scalar cells (A/B) */
+#define FIB_BR_PACKED 1
+#endif
+#ifndef FIB_BR_PACKED_EXACT
+#define FIB_BR_PACKED_EXACT FIB_BR_PACKED
+#endif
 
 namespace fib {
 
@@ -195,7 +201,7 @@ struct BeelerReuter {
   static constexpr int NS = 7;            // C, M, H, J, D, F, XI  (V is the diffusing variable)
   static constexpr int VEC = SLOW ? FIB_BR_VEC_SLOW : FIB_BR_VEC_FAST;
   static constexpr int VEC_SMALL = 1;   // cells per thread on small grids (kSmallGridCells)
-  static constexpr bool PACKED = !FIB_ACCURATE_MATH;   // two cells per thread run as one f2 pair
+  static constexpr bool PACKED = !FIB_ACCURATE_MATH && (CHEBY == 0 ? FIB_BR_PACKED_EXACT : FIB_BR_PACKED);
   static constexpr int BY = 4;
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 2;   // marching depth picked by launch_step (measured best)

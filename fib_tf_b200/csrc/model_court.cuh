@@ -27,6 +27,15 @@
 #ifndef FIB_COURT_MINB_LUT
 #define FIB_COURT_MINB_LUT 4
 #endif
+#ifndef FIB_COURT_PACKED_FAST    /* two cells per thread as one f2 pair; 0 = two scalar cells (A/B) */
+#define FIB_COURT_PACKED_FAST 1
+#endif
+#ifndef FIB_COURT_PACKED_LUT
+#define FIB_COURT_PACKED_LUT 1
+#endif
+#ifndef FIB_COURT_PACKED_ALL
+#define FIB_COURT_PACKED_ALL 1
+#endif
 
 namespace fib {
 
@@ -272,7 +281,8 @@ struct Courtemanche {
   static constexpr int MIN_BLOCKS =
       MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
   static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
-  static constexpr bool PACKED = !FIB_ACCURATE_MATH;   // two cells per thread run as one f2 pair
+  static constexpr bool PACKED = !FIB_ACCURATE_MATH &&
+      (MODE == COURT_FAST ? FIB_COURT_PACKED_FAST : (LUT ? FIB_COURT_PACKED_LUT : FIB_COURT_PACKED_ALL));
   static constexpr bool PREFETCH = false;
   static constexpr bool NEED_RAW = false; // V = enforce_boundary(V0) everywhere (court.py:126-127)
   static constexpr bool NEED_LAP = MODE != COURT_SLOW;

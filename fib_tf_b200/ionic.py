@@ -18,6 +18,9 @@ uses it.  There is no TensorFlow, no XLA and no CPU fallback.
 Extra, optional config keys (all default to the reference's behaviour):
     device       CUDA device ordinal (default: LOCAL_RANK when distributed, else 0)
     graph        replay one CUDA graph per run() iteration (default True)
+    persist      small unsharded 4v / BR grids (W <= 512, the reference's 512^2 configurations): run an
+                 iteration as ONE persistent on-chip kernel, bit-identical to one launch per step
+                 (default True; csrc/fib_persist.cuh)
     distributed  row-shard the grid over the torch.distributed world (default False)
     lut          Courtemanche: V-only intermediates from the 150x30 table (default False)
     probe_batch  headless runs with a cl_observer: the cycle-length probe is recorded on the device
@@ -210,6 +213,8 @@ class IonicModel:
             device = int(os.environ.get('LOCAL_RANK', 0)) if self._nranks > 1 else 0
         if not cfgd.get('graph', True):
             flags |= _capi.F_NO_GRAPH
+        if not cfgd.get('persist', True):
+            flags |= _capi.F_NO_PERSIST
         sharded = self._nranks > 1
         ctx = _capi.Context(self.MODEL_ID, self.height, self.width, self.dt, self.diff, flags=flags,
                             device=device, row0=self._row0 if sharded else 0,

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p build/variants
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
-  ( nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared $flags \
+  ( nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared $flags \
       -o build/variants/lib_$name.so fib_tf_b200/csrc/fib_capi.cu -ldl 2>&1 | grep -E "error" ; echo "built $name" ) &
 done
 wait

@@ -34,8 +34,9 @@ CASES = [
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
+    ncases = int(sys.argv[2]) if len(sys.argv) > 2 else len(CASES)
     out = []
-    for name, cls, N, extra, hole, balg, iters, slow_every in CASES:
+    for name, cls, N, extra, hole, balg, iters, slow_every in CASES[:ncases]:
         cfg = {'width': N, 'height': N, 'dt': 0.1, 'dt_per_plot': 10, 'duration': 1, 'timeline': False,
                'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': False, 'ultra_slow': False}
         cfg.update(extra)

@@ -69,15 +69,19 @@ def main():
         if strict and not (meta0['model'] == 'br' and meta0['config'].get('cheby')):
             continue
         meta, errs, kernel, perr = fixture_errors(name, strict)
-        emit('%s  [%s]  flavour %s' % (name, kernel, onp.flavour_of(meta['model'], meta['config'])))
+        # long-horizon strips (one full action potential, thousands of steps): checked statistically
+        # (activation time, APD, trace) in tests/test_gpu_parity.py, listed here for information only
+        long_h = 'long' in name
+        emit('%s  [%s]  flavour %s%s' % (name, kernel, onp.flavour_of(meta['model'], meta['config']),
+                                        '  (long horizon: informational, checked statistically)' if long_h else ''))
         emit('    %-9s %10s %6s %10s %10s %10s  %s' % ('var', 'rel_err', 'snap', 'noise', 'rounding', 'bar', ''))
         for v in meta['vars']:
             e, i, bar, noise, rnd = errs[v]
             tag = ''
-            if e > 1e-5:
+            if e > 1e-5 and not long_h:
                 tag = 'ABOVE 1e-5' + (' (waived)' if onp.is_waived(meta['model'], meta['config'], v) else '')
                 over_flat.append((name, v, e))
-            if e > bar:
+            if e > bar and not long_h:
                 tag += '  FAIL'
                 failures.append((name, v, e, bar))
             emit('    %-9s %10.3e %6d %10.1e %10.1e %10.1e  %s' % (v, e, i, noise, rnd, bar, tag))

@@ -53,9 +53,11 @@ def test_model_level_helpers_mirror_the_reference_methods(cuda):
     assert np.array_equal(X0, onp.enforce_boundary(X))
     lap = m.laplace(X0)
     want = onp.laplace(X0, m.phase)
-    assert onp.rel_err(lap, want, 1.0) <= 1e-6
+    term = onp.phase_term(np.pad(X0, 1, mode='reflect'), m.phase)
+    # the sums and products are exact replicas; the term's final division is the 2-ulp SFU one
+    assert np.all(np.abs(lap.astype(np.float64) - want) <= 4 * np.spacing(np.abs(term)) + np.spacing(np.abs(want)))
     pf = m.phase_field(np.pad(X0, 1, mode='reflect'))
-    assert onp.rel_err(pf, onp.phase_term(np.pad(X0, 1, mode='reflect'), m.phase), 1e-3) <= 1e-6
+    assert np.all(np.abs(pf.astype(np.float64) - term) <= 4 * np.spacing(np.abs(term)))
     g = rng.uniform(1e-3, 0.998, X.shape).astype(np.float32)
     gi = rng.uniform(0.0, 1.0, X.shape).astype(np.float32)
     tau = rng.uniform(0.05, 500.0, X.shape).astype(np.float32)
@@ -76,7 +78,7 @@ def test_device_probe_ring_reproduces_the_per_iteration_probe(cuda):
     from fib_tf_b200.fenton import Fenton4v
 
     def drive(**kw):
-        cfg = {'width': 96, 'height': 64, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 120,
+        cfg = {'width': 96, 'height': 64, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 420,
                'timeline': False, 'timeline_name': 'x', 'save_graph': False}
         cfg.update(kw)
         m = Fenton4v(cfg)
@@ -87,8 +89,8 @@ def test_device_probe_ring_reproduces_the_per_iteration_probe(cuda):
         m.cl_observer = lambda i, cl: seen.append((i, cl))
         n0 = m._ctx.launch_count()
         for i in m.run(None, block=False):
-            if i == 60:
-                m.fire_op('top')                # rows 0..4 only: re-excites next to the probe row 20
+            if i == 330:
+                m.fire_op('top')                # rows 0..4 only: a second wave towards the probe row 20
         launches = m._ctx.launch_count() - n0
         u = m._State['U'].eval()
         m.close()

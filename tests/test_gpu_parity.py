@@ -86,10 +86,14 @@ def test_long_horizon_apd_and_activation_time(cuda, name):
 METAS = [load_fixture(n)[0] for n in SHORT]
 
 
-def live_tolerance(kind, cfg, var):
-    """Bar for a run that has no fixture of its own: 1e-5, or for a waived variable the rule of
-    oracle.monodomain_np.tolerance with the worst uncertainty the fixtures of that flavour recorded."""
-    return onp.tolerance(kind, cfg, var, *onp.model_uncertainty(METAS, kind, cfg, var))
+def live_tolerance(kind, cfg, var, drift=0.0):
+    """Bar for a run that has no fixture of its own: 1e-5 (for a waived variable the rule of
+    oracle.monodomain_np.tolerance with the worst uncertainty the fixtures of that flavour recorded),
+    but never tighter than 3x `drift` = how far the ORACLE ITSELF moves in this very scenario when
+    every cell is jittered by +-1 ulp after every iteration (onp.ulp_jitter): a stimulus into
+    refractory tissue or a steep wave front amplifies one ulp per step to 1e-5 ... 2e-4 in the
+    Courtemanche gates, and no second fp32 implementation can be closer to the oracle than that."""
+    return max(onp.tolerance(kind, cfg, var, *onp.model_uncertainty(METAS, kind, cfg, var)), 3.0 * drift)
 
 
 @pytest.mark.parametrize('kind,cfg,iters', [
@@ -107,21 +111,25 @@ def test_100_steps_against_live_oracle(cuda, kind, cfg, iters):
             'cheby': False, 'ultra_slow': False}
     base.update(cfg)
     W = base['width']
-    ref, gpu = onp.OracleModel(kind, base), cuda.CudaModel(kind, base)
-    for m in (ref, gpu):
+    ref, jit, gpu = onp.OracleModel(kind, base), onp.OracleModel(kind, base), cuda.CudaModel(kind, base)
+    for m in (ref, jit, gpu):
         m.add_hole(W // 2, W // 2, 30 * W // 512)
         m.define()
         m.add_pace('s2', 'luq', 1.0 if kind == 'fenton4v' else 10.0)
+    rng = np.random.default_rng(1)
     for i in range(iters):
-        for m in (ref, gpu):
+        for m in (ref, jit, gpu):
             m.iterate()
             if kind == 'court' and i % 10 == 0:
                 m.fire('slow')
             if i == iters // 2:
                 m.fire('s2')
+        if i + 1 < iters:
+            onp.ulp_jitter(jit.state, rng)
     for v in ref.state:
-        e = onp.rel_err(gpu.state[v], ref.state[v], onp.var_floor(kind, v))
-        tol = live_tolerance(kind, base, v)
+        fl = onp.var_floor(kind, v)
+        e = onp.rel_err(gpu.state[v], ref.state[v], fl)
+        tol = live_tolerance(kind, base, v, onp.rel_err(jit.state[v], ref.state[v], fl))
         assert e <= tol, '%s %s: rel_err %.3e > %.3e' % (kind, v, e, tol)
     gpu.close()
 

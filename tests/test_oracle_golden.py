@@ -53,3 +53,24 @@ def test_oracle_reproduces_the_start_of_the_512_driver_runs_bitwise(which, kind,
             m.fire('slow')
         got = np.array([m.pot()[r, c] for r, c in meta['probes']], np.float32)
         assert np.array_equal(got, z['probes'][i]), (which, i)
+
+
+def test_waiver_lists_are_the_rule_applied_to_the_fixtures():
+    """oracle.monodomain_np.WAIVERS names exactly the variables whose OWN uncertainty in the reference
+    (max of the libm-swap noise and the float64 distance recorded in the fixtures) reaches 0.7e-5 in
+    some fixture of the flavour; everything else is held to the flat 1e-5 bar."""
+    own = {}
+    for name in golden_names():
+        meta, _ = load_fixture(name)
+        if not meta.get('noise'):
+            continue
+        fl = onp.flavour_of(meta['model'], meta['config'])
+        for key, v in meta['noise'].items():
+            var = key.split('__', 1)[1]
+            d = own.setdefault(fl, {})
+            d[var] = max(d.get(var, 0.0), v, meta['rounding'].get(key, 0.0))
+    derived = {fl: tuple(sorted(v for v, e in d.items() if e >= onp.WAIVE_FROM)) for fl, d in own.items()}
+    derived = {fl: v for fl, v in derived.items() if v}
+    assert derived == {fl: tuple(sorted(w['vars'])) for fl, w in onp.WAIVERS.items()}
+    for fl, w in onp.WAIVERS.items():          # and the caps cover 3x the recorded uncertainty
+        assert all(3 * own[fl][v] <= w['cap'] * 1.0001 for v in w['vars']), fl
