@@ -98,14 +98,15 @@ def pinned_strips(tile, width):
 
 def upload_tiled(ctx, strips, row0, rows, width):
     """Strip-wise H2D upload (from pinned memory) of the mirror-tiled state for global rows
-    [row0, row0+rows): every 512-row block of every plane is one fib_set_rect."""
+    [row0, row0+rows): every 512-row block of every plane is one ENQUEUE-ONLY fib_set_rect_async
+    (no host round trip per strip; the copies are ordered before the first step on the stream)."""
     nbytes = 0
     for name, pinned in strips.items():
         g = row0
         while g < row0 + rows:
             t, r = divmod(g, TILE)
             n = min(TILE - r, row0 + rows - g)
-            ctx.set_rect(name, g, 0, pinned[t & 1][r:r + n])
+            ctx.set_rect_async(name, g, 0, pinned[t & 1][r:r + n])
             nbytes += n * width * 4
             g += n
     return nbytes
@@ -171,9 +172,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's C/OpenMP port on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_sample_run(tile, iterations, budget_s, sample=2048):
+def cpu_sample_run(tile, iterations, budget_s, sample=2048, warmup=1):
     """Times `iterations` run() iterations (10 steps each) of the C port on a sample^2
-    mirror-tiled grid; stops early when the time budget is spent.  -> (gcell_steps_per_s, info)"""
+    mirror-tiled grid after `warmup` untimed ones; stops early when the time budget is spent.
+    -> (gcell_steps_per_s, seconds per iteration, iterations timed, info)"""
     from oracle import cpu_port
     L = cpu_port.port()
     st = tiled_host(tile, sample)
@@ -183,13 +185,13 @@ def cpu_sample_run(tile, iterations, budget_s, sample=2048):
     per_iter = []
     t_all = time.perf_counter()
     done = 0
-    for it in range(iterations + 1):            # first iteration is the warm-up
+    for it in range(iterations + warmup):
         t0 = time.perf_counter()
         for _ in range(10):
             L.fib_cpu_fenton_step(sample, sample, u, t, st['V'], st['W'], st['S'], None, 0.1, 1.5)
             u, t = t, u
         dt = time.perf_counter() - t0
-        if it > 0:
+        if it >= warmup:
             per_iter.append(dt)
             done += 1
         if time.perf_counter() - t_all > budget_s and done >= 1:
@@ -198,23 +200,50 @@ def cpu_sample_run(tile, iterations, budget_s, sample=2048):
     val = sample * sample * 10 / sec / 1e9
     info = {'value': val, 'unit': METRIC, 'cores': int(L.fib_cpu_threads()), 'kind': 'port',
             'sample': 'oracle C/OpenMP port, Fenton 4v %dx%d mirror-tiled spiral, %d iterations x 10 '
-                      'steps (%.2f s/iteration); reference publishes 0.052 Gcell-steps/s for its TF '
-                      'CPU path on a 1.7 GHz quad-core (details.md:264)' % (sample, sample, done, sec),
+                      'steps after %d warm-up (%.2f s/iteration); reference publishes 0.052 Gcell-steps/s for '
+                      'its TF CPU path on a 1.7 GHz quad-core (details.md:264)' % (sample, sample, done, warmup, sec),
             'host_cpus': os.cpu_count()}
     return val, sec, done, info
 
 
-def cpu_tile():
-    """The spiral tile for the CPU legs: from the GPU when there is one, else a committed-free
-    analytic stand-in (throughput is value-independent to first order)."""
-    try:
-        import torch
-        if torch.cuda.is_available():
-            return spiral_tile_gpu(0)
-    except Exception as e:      # noqa: BLE001
-        log('cpu_tile: GPU spiral unavailable (%s); using the S1 initial state' % e)
+def numpy_restatement_baseline(iterations=20):
+    """the reference's CPU path is TensorFlow executing fenton.py's graph on tf.device
+    CPU.  TensorFlow cannot be installed here and /root/reference does not exist on the GPU box, so the
+    closest thing that runs is the oracle's NumPy restatement (oracle/monodomain_np.py: bit-identical to
+    the unmodified reference executed through the NumPy TF facade, tests/test_oracle_golden.py), one
+    core, BASELINE config 1 (4v 512^2 with the hole of fenton.py:169): `iterations` x 10 time steps."""
     from oracle import monodomain_np as onp
-    return onp.fenton_init(TILE, TILE)
+    cfg = fenton_config(TILE, 1)
+    m = onp.OracleModel('fenton4v', cfg)
+    m.add_hole(256, 256, 30)
+    m.define()
+    m.iterate()                                   # warm-up
+    t0 = time.perf_counter()
+    for _ in range(iterations):
+        m.iterate()
+    sec = time.perf_counter() - t0
+    out = {'value': TILE * TILE * 10 * iterations / sec / 1e9, 'unit': METRIC, 'cores': 1,
+           'kind': 'port (NumPy restatement, bit-identical to the reference under the NumPy TF facade)',
+           'sample': 'BASELINE config 1: Fenton 4v 512x512 + hole, %d time steps in %.1f s' % (10 * iterations, sec)}
+    rec = os.path.join(ROOT, 'profiles', 'r2_facade_baseline.json')
+    if os.path.exists(rec):                       # the reference's own solve() under tfshim, timed in the build container
+        out['facade_recorded'] = json.load(open(rec))
+    return out
+
+
+def spiral_tile_cpu():
+    """The developed 512^2 spiral WITHOUT a GPU (the reference arm must not map the product's .so):
+    the S1-S2 protocol of fenton.py:155-185 (no hole) run to 400 ms with the oracle's C/OpenMP port,
+    about 3 s on 16 cores."""
+    from oracle import cpu_port
+    m = cpu_port.CPortModel('fenton4v', fenton_config(TILE, 400))
+    m.define()
+    m.add_pace('s2', 'luq', 1.0)
+    for i in range(400):
+        m.iterate()
+        if i == 210:
+            m.fire('s2')
+    return {n: np.ascontiguousarray(m.state[n]) for n in ('U', 'V', 'W', 'S')}
 
 
 def run_reference_arm(args):
@@ -225,11 +254,12 @@ def run_reference_arm(args):
     # the host threads it can use", so undo that before libgomp is loaded
     if int(os.environ.get('WORLD_SIZE', 1)) > 1 or 'TORCHELASTIC_RUN_ID' in os.environ:
         os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
-    tile = cpu_tile()
-    val, sec, done, info = cpu_sample_run(tile, args.steps, budget_s=150.0)
+    tile = spiral_tile_cpu()
+    W = max(args.warmup, 3)
+    val, sec, done, info = cpu_sample_run(tile, args.steps, budget_s=150.0, warmup=W)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': METRIC, 'n_gpus': args.gpus,
-        'steps': done, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'steps': done, 'warmup': W, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.size, args.gpus),
         'cpu_baseline': info,
@@ -237,7 +267,7 @@ def run_reference_arm(args):
         'gpu_launches': 0,
         'note': 'reference arm = the reference algorithm on host cores (oracle C/OpenMP port; '
                 'TensorFlow is not installable offline); each step is one run() iteration of a '
-                'bounded 2048^2 sample of the workload',
+                'bounded 2048^2 sample of the workload; no GPU and no product code is touched',
     }
     print(json.dumps(line), flush=True)
 
@@ -258,6 +288,69 @@ def workload_config(size, n):
 
 
 # ---------------------------------------------------------------------------------------------
+# the other kernels / BASELINE configurations, device-timed (N = 1 only): `suite` in the JSON line
+# ---------------------------------------------------------------------------------------------
+def run_suite(device, peak, budget_s=40.0):
+    """Device-timed throughput (CUDA events on the library stream, 3 warm-up iterations) of the 4096^2
+    roofline points of every kernel family and of BASELINE configs 1-4 at their own sizes, through the
+    drop-in model classes.  frac = B_alg x Gcell-steps/s / measured HBM peak, B_alg = 8 bytes x state
+    planes (+4 with a phase field) per cell-step."""
+    from fib_tf_b200 import _capi
+    from fib_tf_b200.br import BeelerReuter
+    from fib_tf_b200.court import Courtemanche
+    from fib_tf_b200.court_ultra import Courtemanche as CourtUltra
+    from fib_tf_b200.fenton import Fenton4v
+    cases = [
+        # name, class, N, extra config, hole, B_alg, iterations, slow_every
+        ('config1: 4v 512^2 + hole(256,256,30)', Fenton4v, 512, {'diff': 1.5}, (256, 256, 30), 36, 300, 0),
+        ('config2: BR 512^2 cheby + hole(150,200,40)', BeelerReuter, 512, {'diff': 0.809, 'cheby': True}, (150, 200, 40), 68, 300, 0),
+        ('config3: BR 2048^2 cheby+skip', BeelerReuter, 2048, {'diff': 0.809, 'cheby': True, 'skip': True}, None, 64, 30, 0),
+        ('config4: Courtemanche 2048^2 multi-rate loop (slow every 10)', Courtemanche, 2048, {'diff': 0.809}, None, 168, 60, 10),
+        ('config4: Courtemanche 2048^2 ultra + LUT', CourtUltra, 2048, {'diff': 1.5, 'lut': True}, None, 168, 30, 0),
+        ('4096^2: 4v, one step per launch', Fenton4v, 4096, {'diff': 1.5, 'steps_per_launch': 1}, None, 32, 8, 0),
+        ('4096^2: 4v, two steps per launch', Fenton4v, 4096, {'diff': 1.5, 'steps_per_launch': 2}, None, 32, 8, 0),
+        ('4096^2: BR cheby', BeelerReuter, 4096, {'diff': 0.809, 'cheby': True}, None, 64, 8, 0),
+        ('4096^2: BR exact gates', BeelerReuter, 4096, {'diff': 0.809}, None, 64, 8, 0),
+        ('4096^2: BR cheby+skip', BeelerReuter, 4096, {'diff': 0.809, 'cheby': True, 'skip': True}, None, 64, 8, 0),
+        ('4096^2: Courtemanche ultra', CourtUltra, 4096, {'diff': 1.5}, None, 168, 8, 0),
+        ('4096^2: Courtemanche ultra + LUT', CourtUltra, 4096, {'diff': 1.5, 'lut': True}, None, 168, 8, 0),
+    ]
+    out, t_start = [], time.perf_counter()
+    for name, cls, N, extra, hole, balg, iters, slow_every in cases:
+        if time.perf_counter() - t_start > budget_s:
+            out.append({'case': name, 'skipped': 'suite time budget'})
+            continue
+        cfg = {'width': N, 'height': N, 'dt': 0.1, 'dt_per_plot': 10, 'duration': 1, 'timeline': False,
+               'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': False, 'ultra_slow': False,
+               'device': device}
+        cfg.update(extra)
+        m = cls(cfg)
+        if hole:
+            m.add_hole_to_phase_field(*hole)
+        m.define()
+        c = m._ctx
+
+        def go(n):
+            for i in range(n):
+                c.step(0, 1)
+                if slow_every and i % slow_every == 0:
+                    c.step(1, 1)
+        go(3)
+        c.sync()
+        c.timer_start()
+        go(iters)
+        c.timer_stop()
+        ms = c.timer_ms()
+        steps = iters * m.dt_per_step
+        g = N * N * steps / (ms * 1e-3) / 1e9
+        out.append({'case': name, 'grid': [N, N], 'time_steps': steps, 'us_per_time_step': ms * 1e3 / steps,
+                    'value': g, 'unit': METRIC, 'bytes_per_cell_step': balg, 'frac': g * balg / peak,
+                    'kernel': _capi.last_kernel(), 'l2_resident': N * N * 4 * c.nvars < 100e6})
+        m.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -268,6 +361,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--size', type=int, default=32768)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-suite', action='store_true', help='skip the per-kernel suite (N = 1)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -320,14 +414,26 @@ def main():
     sampler.start()
     ctx.step(0, Wm)                                     # warm-up (also instantiates the graph)
     barrier()
-    n0 = ctx.launch_count()
-    ctx.timer_start()
-    ctx.step(0, K)
-    ctx.timer_stop()
-    ms_dev = ctx.timer_ms()
-    barrier()
-    launches_rank = ctx.launch_count() - n0
-    ms = max_over_ranks(ms_dev)
+    # EXACTLY K steps per timed region, bracketed by barrier + synchronize.  A region shorter than
+    # 0.5 s (8 GPUs: ~0.1 s) is repeated back to back and the MEAN of the repetitions is reported.
+    reps, ms_list, ms_dev_list, launches_rank = 1, [], [], 0
+    r = 0
+    while r < reps:
+        n0 = ctx.launch_count()
+        ctx.timer_start()
+        ctx.step(0, K)
+        ctx.timer_stop()
+        ms_dev = ctx.timer_ms()
+        barrier()
+        launches_rank = ctx.launch_count() - n0
+        ms_r = max_over_ranks(ms_dev)
+        ms_list.append(ms_r)
+        ms_dev_list.append(ms_dev)
+        if r == 0 and ms_r < 500.0:
+            reps = min(int(np.ceil(500.0 / max(ms_r, 1e-3))), 20)
+        r += 1
+    ms = float(np.mean(ms_list))
+    ms_dev = float(np.mean(ms_dev_list))
     launches = int(sum_over_ranks(launches_rank))
     cells = float(size) * size
     value = cells * K * 10 / (ms * 1e-3) / 1e9
@@ -368,14 +474,22 @@ def main():
     spl = int(getattr(model, 'steps_per_launch_used', 1))
     launch_ms = ms_dev / (K * 10)
     achieved = B_ALG * rows * size / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    # `traffic`: DRAM bytes PER LAUNCH of the dominant kernel = ncu dram__bytes_read.sum + write.sum per
+    # cell and time step (profiles/traffic.json, one `ncu --set full` capture of this kernel at 4096^2)
+    # x the cells and the time steps one launch of this rank covers.  dram_frac = that traffic / the
+    # launch duration measured here / the HBM peak: how busy HBM really is (frac, on the ALGORITHMIC
+    # 32 B per cell-step, exceeds 1 with two steps per launch because the planes move once per two steps).
+    traffic, dram_frac, traffic_src = None, None, None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get('fenton4v_fused2_step' if spl == 2 else 'fenton4v_step')
         if tj:
-            traffic = tj['dram_bytes_per_cell'] * rows * size
+            traffic = tj['dram_bytes_per_cell'] * rows * size * spl
+            dram_frac = traffic / (launch_ms * spl * 1e-3) / 1e9 / peak
+            traffic_src = 'profiles/traffic.json: %s B per cell and time step (ncu --set full)' % tj['dram_bytes_per_cell']
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'dram_frac': dram_frac,
+                'traffic_source': traffic_src, 'peak_source': peak_src,
                 'kernel': 'fib::fenton_fused2_kernel (2 time steps per launch)' if spl == 2
                           else 'fib::step_kernel<Fenton4v,...>',
                 'bytes_per_cell_step': B_ALG, 'time_steps_per_launch': spl,
@@ -390,9 +504,13 @@ def main():
         'e2e': {'value': e2e_value, 'unit': METRIC, 'h2d_bytes_per_step': sum_over_ranks(h2d) / K,
                 'd2h_bytes_per_step': sum_over_ranks(d2h) / K, 'seconds': e2e_s},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        'timed_regions': {'repeats': reps, 'ms_each': ms_list},
     }
+    if rank == 0 and world == 1 and not args.no_suite:
+        line['suite'] = run_suite(local, peak)
     if rank == 0 and world == 1 and not args.no_cpu:
-        _v, _s, _d, info = cpu_sample_run(tile, 8, budget_s=20.0)
+        _v, _s, _d, info = cpu_sample_run(tile, 8, budget_s=20.0, warmup=3)
+        info['numpy_restatement'] = numpy_restatement_baseline()
         line['cpu_baseline'] = info
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -1078,8 +1078,9 @@ static void decide_persist(fib_ctx* c) {
   if (!ok) return;
   const int tiles = (c->g.H + th - 1) / th;
   if (!c->pflags) {
-    if (cudaMalloc(&c->pflags, sizeof(unsigned) * (size_t)c->sms * 2) != cudaSuccess) { cudaGetLastError(); return; }
-    cudaMemsetAsync(c->pflags, 0, sizeof(unsigned) * (size_t)c->sms * 2, c->stream);
+    const size_t fbytes = sizeof(unsigned) * (size_t)(c->sms + 2) * kFlagStride;
+    if (cudaMalloc(&c->pflags, fbytes) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemsetAsync(c->pflags, 0, fbytes, c->stream);
     if (cudaHostAlloc(&c->perr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
     *c->perr = 0;
   }

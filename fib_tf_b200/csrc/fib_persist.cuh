@@ -39,6 +39,7 @@ constexpr int kPersistThreads = 512;      // one thread per column: W <= 512
 constexpr int kPersistBox = 256;          // TMA box width (elements; the hardware limit per dimension)
 constexpr int kPersistWP = 512 + 64;      // padded row of the diffusing tile: data at +32 floats (128 B)
 constexpr unsigned kSpinLimit = 1u << 22;
+constexpr int kFlagStride = 32;           // one 128-B line per tile's step counter (no false sharing)
 
 // ---- PTX wrappers: mbarrier + TMA (SASS: SYNCS / UTMALDG / UTMASTG) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -102,7 +103,7 @@ struct PersistArgs {
   int cur;                     // x[cur] holds the state at the start of the launch
   int nsteps;                  // time steps of this launch (dt_per_step)
   unsigned char slow[kPersistMaxSteps];   // per step: 1 -> MS (e.g. BR n > 0), 0 -> MF (BR n == 0)
-  unsigned* flags;             // [tiles] steps published so far (monotonic over the whole run)
+  unsigned* flags;             // [tiles * kFlagStride] steps published so far (monotonic over the whole run)
   unsigned base;               // value of every flag at the start of this launch
   int* err;                    // set to 1 if a neighbour wait ran into the spin limit
   const float* phase;          // halo layout (one row), or nullptr
@@ -204,8 +205,14 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     // neighbour rows (the ring): global rows r0 - 1 and r0 + TH, columns c-1, c, c+1 (clamped)
     float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
     const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
+    // ONE lane per warp polls (two L2 requests per warp and poll, each counter on its own line) and
+    // broadcasts; the acquire orders the ring loads of the whole warp behind it (__shfl_sync converges it)
     auto ring_ready = [&]() {
-      return (!need_top || ld_acquire(a.flags + tile - 1) >= want) && (!need_bot || ld_acquire(a.flags + tile + 1) >= want);
+      int ok = 1;
+      if ((t & 31) == 0)
+        ok = (!need_top || ld_acquire(a.flags + (tile - 1) * kFlagStride) >= want) &&
+             (!need_bot || ld_acquire(a.flags + (tile + 1) * kFlagStride) >= want);
+      return __shfl_sync(0xffffffffu, ok, 0) != 0;
     };
     auto ring_load = [&]() {
       if (!active) return;
@@ -253,6 +260,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       unsigned spins = 0;
       while (!ring_ready()) {
         if (++spins > kSpinLimit) { *a.err = 1; break; }
+        __nanosleep(40);
       }
       ring_load();
     }
@@ -268,10 +276,9 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       }
     }
     __syncthreads();            // shared tile of the next step complete; all edge stores issued
-    if (t == 0) {
-      __threadfence();
-      st_release(a.flags + tile, want + 1);
-    }
+    // release: the edge stores of all threads happen-before the barrier, the barrier before this store
+    // (cumulativity); the neighbours' acquire loads then see them
+    if (t == 0) st_release(a.flags + tile * kFlagStride, want + 1);
   }
 
   // ---- TMA out: registers -> staging, then tile stores (rows beyond the grid are clipped)

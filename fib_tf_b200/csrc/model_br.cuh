@@ -26,7 +26,7 @@
 #define FIB_BR_MINB_SLOW 7
 #endif
 #ifndef FIB_BR_MINB_SLOW_EXACT
-#define FIB_BR_MINB_SLOW_EXACT 7
+#define FIB_BR_MINB_SLOW_EXACT 5   /* packed pairs want registers: 4 / 5 / 6 / 7 CTAs -> 77.9 / 79.3 / 77.1 / 60.8 */
 #endif
 #ifndef FIB_BR_VEC_FAST
 #define FIB_BR_VEC_FAST 2

@@ -5,15 +5,18 @@
 #pragma once
 #include "fib_kernels.cuh"
 
-// cells per thread / resident CTAs per SM per kernel flavour, measured on B200 (4096^2):
-//   fast op   1 cell @12 CTAs 69.6 -> 2 cells @8 CTAs 80.6 Gcell-steps/s
-//   all-state 1 cell @8 CTAs 28.4 (2 cells @3-4 CTAs: 23.8-27.5)
-//   LUT       1 cell @5 CTAs 30.0 -> 2 cells @4 CTAs 33.3
+// cells per thread / resident CTAs per SM / packed pairs per kernel flavour, measured on B200 (4096^2,
+// Gcell-steps/s; profiles/r2_tuning_log.md):
+//   fast op   2 scalar cells @8 CTAs 78.3 (packed pair @6/8/10: 73.5 / 75.2 / 55.7: HBM-bound, packing only
+//             costs registers)
+//   all-state 1 cell @8 CTAs 28.0 -> packed pair @4 CTAs 32.7 -> @5 CTAs 34.8 (89 % of the 168-B roofline)
+//   LUT       packed pair @4/5/6 CTAs 32.2 / 33.1 / 31.1; 2 scalar cells @4 CTAs 34.1 -> @5 CTAs 36.6 (94 %):
+//             the table flavour is load-bound (60 table reads per pair), the pair registers do not pay
 #ifndef FIB_COURT_VEC_FAST
 #define FIB_COURT_VEC_FAST 2
 #endif
 #ifndef FIB_COURT_VEC_ALL
-#define FIB_COURT_VEC_ALL 1
+#define FIB_COURT_VEC_ALL 2
 #endif
 #ifndef FIB_COURT_VEC_LUT
 #define FIB_COURT_VEC_LUT 2
@@ -22,16 +25,16 @@
 #define FIB_COURT_MINB_FAST 8
 #endif
 #ifndef FIB_COURT_MINB_ALL
-#define FIB_COURT_MINB_ALL 8
+#define FIB_COURT_MINB_ALL 5
 #endif
 #ifndef FIB_COURT_MINB_LUT
-#define FIB_COURT_MINB_LUT 4
+#define FIB_COURT_MINB_LUT 5
 #endif
 #ifndef FIB_COURT_PACKED_FAST    /* two cells per thread as one f2 pair; 0 = two scalar cells (A/B) */
-#define FIB_COURT_PACKED_FAST 1
+#define FIB_COURT_PACKED_FAST 0
 #endif
 #ifndef FIB_COURT_PACKED_LUT
-#define FIB_COURT_PACKED_LUT 1
+#define FIB_COURT_PACKED_LUT 0
 #endif
 #ifndef FIB_COURT_PACKED_ALL
 #define FIB_COURT_PACKED_ALL 1
@@ -280,7 +283,10 @@ struct Courtemanche {
   static constexpr int AUTO_R = LUT ? 2 : 1;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS =
       MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
-  static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
+  // the one-cell-per-thread flavour of the direct all-state kernel (small grids) keeps 8 CTAs per SM
+  static __host__ __device__ constexpr int min_blocks(int vec) {
+    return (MODE == COURT_ALL && !LUT && vec == 1) ? 8 : MIN_BLOCKS;
+  }
   static constexpr bool PACKED = !FIB_ACCURATE_MATH &&
       (MODE == COURT_FAST ? FIB_COURT_PACKED_FAST : (LUT ? FIB_COURT_PACKED_LUT : FIB_COURT_PACKED_ALL));
   static constexpr bool PREFETCH = false;

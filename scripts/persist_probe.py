@@ -1,0 +1,27 @@
+"""Small driver for profiling the persistent kernel: BASELINE configs 1 / 2 for a few iterations.
+    python scripts/persist_probe.py [4v|br] [iterations]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fib_tf_b200.br import BeelerReuter  # noqa: E402
+from fib_tf_b200.fenton import Fenton4v  # noqa: E402
+
+kind = sys.argv[1] if len(sys.argv) > 1 else '4v'
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+cfg = {'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5 if kind == '4v' else 0.809,
+       'duration': 1, 'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': True}
+m = (Fenton4v if kind == '4v' else BeelerReuter)(cfg)
+m.add_hole_to_phase_field(*((256, 256, 30) if kind == '4v' else (150, 200, 40)))
+m.define()
+c = m._ctx
+c.step(0, 3)
+c.sync()
+c.timer_start()
+c.step(0, iters)
+c.timer_stop()
+ms = c.timer_ms()
+steps = iters * m.dt_per_step
+print('%s 512^2: %.2f us per time step, %.1f Gcell-steps/s (%d launches)' % (
+    kind, ms * 1e3 / steps, 512 * 512 * steps / ms / 1e6, c.launch_count()))
+m.close()

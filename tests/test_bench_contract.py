@@ -49,7 +49,7 @@ def test_our_arm_prints_one_contract_line(cuda_device):
     the contract, the device-timed value consistent with ms_per_step, a non-trivial e2e leg and
     kernels of this library launched inside the timed region."""
     p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--size', '4096', '--steps', '3',
-                        '--warmup', '3', '--no-cpu'], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        '--warmup', '3', '--no-cpu', '--no-suite'], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
     assert len(lines) == 1

@@ -52,6 +52,7 @@ def test_fenton_persistent_kernel_is_bit_identical(cuda, H, W, th, hole):
     init['U'][H // 3:H // 2 + 1, W // 4:W // 2] = 0.95
     per, ref = _pair(_capi.FENTON4V, H, W, 0.1, 1.5, 0, init, _phase(H, W) if hole else None, None)
     stim = ('U', 1, max(H - 1, 2), 1, max(W // 2, 2), 0.6, 0.0)
+    n_per, n_ref = per.launch_count(), ref.launch_count()
     for it in range(4):
         per.step(0, 1)
         ref.step(0, 1)
@@ -68,7 +69,8 @@ def test_fenton_persistent_kernel_is_bit_identical(cuda, H, W, th, hole):
         want = ref.get_state(v)
         assert np.isfinite(want).all()
         assert np.array_equal(per.get_state(v), want), v
-    assert per.launch_count() == 7 + 1 and ref.launch_count() == 70 + 1       # ONE launch per iteration (+ the stimulus)
+    # ONE launch per iteration (+ the stimulus kernel)
+    assert per.launch_count() - n_per == 7 + 1 and ref.launch_count() - n_ref == 70 + 1
     per.close()
     ref.close()
 
@@ -90,6 +92,7 @@ def test_beeler_reuter_persistent_kernel_is_bit_identical(cuda, H, W, th, hole, 
         init[g] = rng.uniform(1e-3, 0.998, (H, W)).astype(np.float32)
     per, ref = _pair(_capi.BR, H, W, 0.1, 0.809, fl, init, _phase(H, W) if hole else None, table)
     stim = ('V', 1, max(H // 2, 2), 1, max(W // 2, 2), 10.0, -90.0)
+    n_per, n_ref = per.launch_count(), ref.launch_count()
     for it in range(5):
         per.step(0, 1)
         ref.step(0, 1)
@@ -106,7 +109,7 @@ def test_beeler_reuter_persistent_kernel_is_bit_identical(cuda, H, W, th, hole, 
     for v in ref.var_names:
         a, b = per.get_state(v), ref.get_state(v)
         assert np.array_equal(a, b, equal_nan=True), (v, float(np.nanmax(np.abs(a - b))))
-    assert per.launch_count() == 7 and ref.launch_count() == 31
+    assert per.launch_count() - n_per == 6 + 1 and ref.launch_count() - n_ref == 30 + 1
     per.close()
     ref.close()
 
