@@ -142,6 +142,7 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
         ph = phase_flag(j);
         if (ph) load_phi(j, pN, pS, pC);
       }
+      float lapv[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         float lap = lap9(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], xN[l], xS[l], xN[l + 2],
@@ -149,10 +150,9 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
         if (PHASE && ph)
           lap = __fadd_rn(lap, phase_term(xN[l + 1], xS[l + 1], xC[l], xC[l + 2], pN[l], pS[l],
                                           pC[l], pC[l + 2], pC[l + 1]));
-        float sl[3] = {sQ[0][l], sQ[1][l], sQ[2][l]};
-        Fenton4v::cell(sa, xraw[l], xC[l + 1], lap, sl, u1[l]);
-        sQ[0][l] = sl[0]; sQ[1][l] = sl[1]; sQ[2][l] = sl[2];
+        lapv[l] = lap;
       }
+      Fenton4v::cell4(sa, xraw, &xC[1], lapv, sQ, u1);
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) { xN[q] = xC[q]; xC[q] = xS[q]; }
@@ -195,7 +195,7 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
         ph = phase_flag(r);
         if (ph) load_phi(r, pN, pS, pC);
       }
-      float u2[4];
+      float u2[4], lapv[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         float lap = lap9(nN[l + 1], nS[l + 1], nC[l], nC[l + 2], nN[l], nS[l], nN[l + 2],
@@ -203,11 +203,10 @@ fenton_fused2_kernel(const Geom g, const Fused2Args a) {
         if (PHASE && ph)
           lap = __fadd_rn(lap, phase_term(nN[l + 1], nS[l + 1], nC[l], nC[l + 2], pN[l], pS[l],
                                           pC[l], pC[l + 2], pC[l + 1]));
-        const float raw = l == 0 ? eB[0] : (l == 3 ? eB[1] : wB[l + 1]);
-        float sl[3] = {sP[0][l], sP[1][l], sP[2][l]};
-        Fenton4v::cell(sa, raw, nC[l + 1], lap, sl, u2[l]);
-        sP[0][l] = sl[0]; sP[1][l] = sl[1]; sP[2][l] = sl[2];
+        lapv[l] = lap;
       }
+      const float raw2[4] = {eB[0], wB[2], wB[3], eB[1]};
+      Fenton4v::cell4(sa, raw2, &nC[1], lapv, sP, u2);
       if (emit_lane) {
         const int off = rowoff(r) + c;
         VecIO<4>::st(a.out[0] + off, u2);

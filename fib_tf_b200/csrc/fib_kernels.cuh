@@ -146,19 +146,22 @@ step_kernel(const Geom g, const StepArgs<M> a) {
         }
         lapv[l] = lap;
       }
-      if constexpr (M::PACKED && VEC == 2) {
-        // two cells per thread as ONE packed pair: every multiply-add of the ionic update is a single
-        // FFMA2 / FMUL2 / FADD2 for both cells (fib_math.cuh); per lane the arithmetic is that of the
+      if constexpr (M::PACKED && VEC % 2 == 0) {
+        // the cells of a thread as packed PAIRS: every multiply-add of the ionic update is a single
+        // FFMA2 / FMUL2 / FADD2 for two cells (fib_math.cuh); per lane the arithmetic is that of the
         // scalar flavour of the same source
-        f2 sp[M::NS > 0 ? M::NS : 1];
 #pragma unroll
-        for (int k = 0; k < M::NS; ++k) sp[k] = f2(sv[k][0], sv[k][VEC - 1]);
-        f2 xn;
-        M::cell(a, f2(xraw[0], xraw[VEC - 1]), f2(xC[1], xC[VEC]), f2(lapv[0], lapv[VEC - 1]), sp, xn);
-        xnew[0] = xn.x;
-        xnew[VEC - 1] = xn.y;
+        for (int l = 0; l < VEC; l += 2) {
+          f2 sp[M::NS > 0 ? M::NS : 1];
 #pragma unroll
-        for (int k = 0; k < M::NS; ++k) { sv[k][0] = sp[k].x; sv[k][VEC - 1] = sp[k].y; }
+          for (int k = 0; k < M::NS; ++k) sp[k] = f2(sv[k][l], sv[k][l + 1]);
+          f2 xn;
+          M::cell(a, f2(xraw[l], xraw[l + 1]), f2(xC[l + 1], xC[l + 2]), f2(lapv[l], lapv[l + 1]), sp, xn);
+          xnew[l] = xn.x;
+          xnew[l + 1] = xn.y;
+#pragma unroll
+          for (int k = 0; k < M::NS; ++k) { sv[k][l] = sp[k].x; sv[k][l + 1] = sp[k].y; }
+        }
       } else {
 #pragma unroll
         for (int l = 0; l < VEC; ++l) {

@@ -6,6 +6,9 @@
 #ifndef FIB_4V_MINB
 #define FIB_4V_MINB 8
 #endif
+#ifndef FIB_4V_PACKED           /* the four cells of a thread as two f2 pairs (packed fp32) */
+#define FIB_4V_PACKED 1
+#endif
 
 namespace fib {
 
@@ -18,7 +21,7 @@ struct Fenton4v {
   static constexpr int AUTO_R = 4;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS = FIB_4V_MINB;
   static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
-  static constexpr bool PACKED = false;   // HBM-bound already: scalar cells, four per thread
+  static constexpr bool PACKED = FIB_4V_PACKED != 0;   // the four cells of a thread as two f2 pairs
   static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
   static constexpr bool NEED_LAP = true;
@@ -34,45 +37,72 @@ struct Fenton4v {
 
   // Divisions by literals are multiplications by the correctly rounded reciprocal (<= 1 ulp from
   // the reference's fp32 division; budgeted in SURVEY.md Appendix B.2).
-  static __device__ __forceinline__ void cell(const StepArgs<Fenton4v>& a, float U, float U0,
-                                              float lap, float (&s)[NS], float& Unew) {
+  // Generic over T = float (one cell) and T = f2 (two cells as one packed pair: FFMA2 / FMUL2 / FADD2,
+  // fib_math.cuh); every operation is spelled with its own rounding (mul_rn / add_rn / vfma), so a lane of
+  // the pair computes exactly what the scalar cell computes and every kernel that calls this function --
+  // one step per launch, two steps per launch, the persistent kernel -- agrees bit for bit.
+  template <class T>
+  static __device__ __forceinline__ void cell(const StepArgs<Fenton4v>& a, T U, T U0, T lap, T (&s)[NS],
+                                              T& Unew) {
     constexpr float tau_vp = 3.33f, tau_vn = 19.2f, tau_wp = 160.0f, tau_wn = 75.0f;
     constexpr float tau_d = 0.065f, tau_si = 31.8364f, tau_so = 31.8364f, tau_a = 0.009f;
     constexpr float u_c = 0.23f, u_m = 1.0f, u_csi = 0.8f, u_so = 0.3f;
     constexpr float r_sn = 1.2f, k_ = 3.0f, b_so = 0.84f, c_so = 0.02f;
     constexpr float c_so_half = (float)(0.5 * (0.115 - 0.009));   // 0.5*(a_so - tau_a), fenton.py:83
     constexpr float r_diff = (float)(0.02 - 1.2);                 // (r_sp - r_sn),      fenton.py:89
-    const float dt = a.p.dt;
-    float V = s[0], W = s[1], S = s[2];
+    const T dt = T(a.p.dt);
+    const T V = s[0], W = s[1], S = s[2];
 
     // H(x) = (1+sign x)/2, G(x) = (1-sign x)/2 (fenton.py:73-79): 0.5 at x == 0
-    const float Hc = U > u_c ? 1.f : (U < u_c ? 0.f : 0.5f);
-    const float Hso = U > u_so ? 1.f : (U < u_so ? 0.f : 0.5f);
-    const float Gso = 1.f - Hso;
+    const auto above_c = gt(U, T(u_c));
+    const T Hc = sel(above_c, T(1.f), sel(lt(U, T(u_c)), T(0.f), T(0.5f)));
+    const T Hso = sel(gt(U, T(u_so)), T(1.f), sel(lt(U, T(u_so)), T(0.f), T(0.5f)));
+    const T Gso = sub_rn(T(1.f), Hso);
 
-    // Every multiply-add below is spelled out (fmaf / __f*_rn): whether ptxas fuses a free-standing
-    // multiply and add depends on the surrounding kernel, and the two-steps-per-launch kernel
-    // (fib_fused.cuh) must reproduce this one bit for bit.
-    const float X_fi = __fmul_rn(__fmul_rn(__fmul_rn(-V, Hc), U - u_c), u_m - U);
-    const float I_si = __fmul_rn(__fmul_rn(-W, S), 1.0f / tau_si);
+    const T X_fi = mul_rn(mul_rn(mul_rn(-V, Hc), sub_rn(U, T(u_c))), sub_rn(T(u_m), U));
+    const T I_si = mul_rn(mul_rn(-W, S), T(1.0f / tau_si));
     // 0.5 (a_so - tau_a) (1 + tanh z) = (a_so - tau_a) * [0.5 (1 + tanh z)]
-    const float T_so = m_half_1p_tanh(__fmul_rn(U - b_so, 1.0f / c_so));
-    const float I_so = fmaf(2.0f * c_so_half, T_so,
-                            fmaf(__fmul_rn(U, Gso), 1.0f / tau_so, __fmul_rn(Hso, tau_a)));
+    const T T_so = m_half_1p_tanh(mul_rn(sub_rn(U, T(b_so)), T(1.0f / c_so)));
+    const T I_so = vfma(T(2.0f * c_so_half), T_so,
+                        vfma(mul_rn(U, Gso), T(1.0f / tau_so), mul_rn(Hso, T(tau_a))));
     // dU = -(I_fi + I_si + I_so), I_fi = X_fi / tau_d
-    const float dU = -__fadd_rn(fmaf(X_fi, 1.0f / tau_d, I_si), I_so);
-    const float dV = U > u_c ? __fmul_rn(-V, 1.0f / tau_vp) : __fmul_rn(1.f - V, 1.0f / tau_vn);
+    const T dU = -add_rn(vfma(X_fi, T(1.0f / tau_d), I_si), I_so);
+    const T dV = sel(above_c, mul_rn(-V, T(1.0f / tau_vp)), mul_rn(sub_rn(T(1.f), V), T(1.0f / tau_vn)));
     // tau_wn1 == tau_wn2 == 75 (fenton.py:53-54): the inner tf.where is an identity
-    const float dW = U > u_c ? __fmul_rn(-W, 1.0f / tau_wp) : __fmul_rn(1.f - W, 1.0f / tau_wn);
-    const float r_s = fmaf(r_diff, Hc, r_sn);
-    const float dS = __fmul_rn(r_s, m_half_1p_tanh(__fmul_rn(U - u_csi, k_)) - S);
+    const T dW = sel(above_c, mul_rn(-W, T(1.0f / tau_wp)), mul_rn(sub_rn(T(1.f), W), T(1.0f / tau_wn)));
+    const T r_s = vfma(T(r_diff), Hc, T(r_sn));
+    const T dS = mul_rn(r_s, sub_rn(m_half_1p_tanh(mul_rn(sub_rn(U, T(u_csi)), T(k_))), S));
 
     // (U0 + dt*dU) + ddt*lap with the reference's rounding sequence (fenton.py:103): near U ~ 0 an
     // FMA's missing rounding would show up as a 1-ulp(|U0|) absolute difference
-    Unew = __fadd_rn(__fadd_rn(U0, __fmul_rn(dt, dU)), __fmul_rn(a.p.ddt, lap));
-    s[0] = fmaf(dt, dV, V);
-    s[1] = fmaf(dt, dW, W);
-    s[2] = fmaf(dt, dS, S);
+    Unew = add_rn(add_rn(U0, mul_rn(dt, dU)), mul_rn(T(a.p.ddt), lap));
+    s[0] = vfma(dt, dV, V);
+    s[1] = vfma(dt, dW, W);
+    s[2] = vfma(dt, dS, S);
+  }
+
+  // four cells of a thread: two packed pairs (FIB_4V_PACKED, default) or four scalar cells
+  static __device__ __forceinline__ void cell4(const StepArgs<Fenton4v>& a, const float (&raw)[4], const float* x0,
+                                               const float (&lap)[4], float (&sv)[3][4], float (&unew)[4]) {
+#if FIB_4V_PACKED
+#pragma unroll
+    for (int l = 0; l < 4; l += 2) {
+      f2 sp[3] = {f2(sv[0][l], sv[0][l + 1]), f2(sv[1][l], sv[1][l + 1]), f2(sv[2][l], sv[2][l + 1])};
+      f2 un;
+      cell(a, f2(raw[l], raw[l + 1]), f2(x0[l], x0[l + 1]), f2(lap[l], lap[l + 1]), sp, un);
+      unew[l] = un.x;
+      unew[l + 1] = un.y;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { sv[k][l] = sp[k].x; sv[k][l + 1] = sp[k].y; }
+    }
+#else
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      float sl[3] = {sv[0][l], sv[1][l], sv[2][l]};
+      cell(a, raw[l], x0[l], lap[l], sl, unew[l]);
+      sv[0][l] = sl[0]; sv[1][l] = sl[1]; sv[2][l] = sl[2];
+    }
+#endif
   }
 };
 
