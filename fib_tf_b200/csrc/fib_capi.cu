@@ -808,7 +808,9 @@ extern "C" int fib_court_inter(fib_ctx* c, const float* v_host, size_t n, float*
 // the step schedule
 // ------------------------------------------------------------------------------------------
 static int substeps_of(const fib_ctx* c, int op) {
-  if (op == FIB_OP_ODE) return c->dt_per_step;
+  // FIB_DEBUG_SUBSTEPS=n: run only the first n time steps of an iteration (diagnostics only)
+  static const int dbg = getenv("FIB_DEBUG_SUBSTEPS") ? atoi(getenv("FIB_DEBUG_SUBSTEPS")) : 0;
+  if (op == FIB_OP_ODE) return (dbg > 0 && dbg < c->dt_per_step) ? dbg : c->dt_per_step;
   return c->cfg.model == FIB_COURT ? 1 : 0;   // 'slow' is an empty group elsewhere
 }
 
@@ -1097,7 +1099,7 @@ static int run_iteration_persist(fib_ctx* c) {
   cudaError_t e;
   if (c->cfg.model == FIB_FENTON4V) {
     PersistArgs<Fenton4v, Fenton4v> a;
-    for (int i = 0; i < kPersistMaxSteps; ++i) a.slow[i] = 1;
+    a.slow_mask = ~0u;
     a.ps.dt = a.pf.dt = (float)dt;
     a.ps.ddt = a.pf.ddt = (float)(c->cfg.diff * dt);
     e = launch_persist_m<Fenton4v, Fenton4v>(c, a, 8);
@@ -1108,7 +1110,7 @@ static int run_iteration_persist(fib_ctx* c) {
       using MS = decltype(ts);
       using MF = decltype(tf);
       PersistArgs<MS, MF> a;
-      for (int i = 0; i < kPersistMaxSteps; ++i) a.slow[i] = skip ? (i == 0) : 1;     // br.py:96-107
+      a.slow_mask = skip ? 1u : ~0u;                                                  // br.py:96-107
       auto fill = [&](auto& p, int n) {
         p.dt = (float)dt;
         p.neg_dt = (float)(-dt);

@@ -79,11 +79,14 @@ __device__ __forceinline__ void tma_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+// Polling load: relaxed at gpu scope (L2).  ld.acquire would add a CCTL.IVALL -- an invalidation of the
+// whole L1 -- to EVERY poll; instead the poll is relaxed and ONE acquire fence follows the successful one.
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -102,7 +105,7 @@ struct PersistArgs {
   float* x[2];                 // the same two buffers as plain pointers (halo layout: row g at (g + 1) * pitch)
   int cur;                     // x[cur] holds the state at the start of the launch
   int nsteps;                  // time steps of this launch (dt_per_step)
-  unsigned char slow[kPersistMaxSteps];   // per step: 1 -> MS (e.g. BR n > 0), 0 -> MF (BR n == 0)
+  unsigned slow_mask;          // bit s: step s is an MS step (e.g. BR n > 0), else MF (BR n == 0)
   unsigned* flags;             // [tiles * kFlagStride] steps published so far (monotonic over the whole run)
   unsigned base;               // value of every flag at the start of this launch
   int* err;                    // set to 1 if a neighbour wait ran into the spin limit
@@ -173,10 +176,9 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
   sa_s.p = a.ps;
   sa_f.p = a.pf;
 
-  // one cell: exactly step_kernel's arithmetic.  nN / nC / nS: the clamped-column triples of the
-  // enforced rows above / at / below; raw: the un-enforced centre value.
-  auto advance = [&](bool slow, int i, const float (&nN)[3], const float (&nC)[3], const float (&nS)[3],
-                     float raw) -> float {
+  // Laplacian (+ phase term) of row i: exactly step_kernel's arithmetic.  nN / nC / nS: the clamped-column
+  // triples of the enforced rows above / at / below.
+  auto lap_row = [&](int i, const float (&nN)[3], const float (&nC)[3], const float (&nS)[3]) -> float {
     float lap = lap9(nN[1], nS[1], nC[0], nC[2], nN[0], nS[0], nN[2], nS[2], nC[1]);
     if (PHASE && ((phbits >> i) & 1u)) {
       const int gr = r0 + i;
@@ -186,13 +188,28 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       const float pW = ph[rC + clampi(reflecti(c - 1, W), 0, W - 1)], pE = ph[rC + clampi(reflecti(c + 1, W), 0, W - 1)];
       lap = __fadd_rn(lap, phase_term(nN[1], nS[1], nC[0], nC[2], pN, pS, pW, pE, ph[rC + c]));
     }
+    return lap;
+  };
+  // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
+  // model's cell function; raw: the un-enforced centre value, x0: the enforced one
+  auto advance = [&](bool slow, int i, float raw, float x0, float lap) -> float {
     float sl[NS], xnew;
 #pragma unroll
     for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
-    if (slow) MS::cell(sa_s, raw, nC[1], lap, sl, xnew);
-    else MF::cell(sa_f, raw, nC[1], lap, sl, xnew);
+    if (slow) MS::cell(sa_s, raw, x0, lap, sl, xnew);
+    else MF::cell(sa_f, raw, x0, lap, sl, xnew);
 #pragma unroll
     for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
+    return xnew;
+  };
+  auto advance2 = [&](bool slow, int i, int j, f2 raw, f2 x0, f2 lap) -> f2 {
+    f2 sl[NS], xnew;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
+    if (slow) MS::cell(sa_s, raw, x0, lap, sl, xnew);
+    else MF::cell(sa_f, raw, x0, lap, sl, xnew);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) { s[k][i] = sl[k].x; s[k][j] = sl[k].y; }
     return xnew;
   };
 
@@ -200,18 +217,18 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     const int p = step & 1;                                  // shared buffer holding the state at this step
     const float* xg = a.x[(a.cur + step) & 1];               // global plane with the neighbours' edge rows of it
     float* xg_next = a.x[(a.cur + step + 1) & 1];
-    const bool slow = a.slow[step] != 0;
+    const bool slow = (a.slow_mask >> step) & 1u;
     const unsigned want = a.base + step;
     // neighbour rows (the ring): global rows r0 - 1 and r0 + TH, columns c-1, c, c+1 (clamped)
     float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
     const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
-    // ONE lane per warp polls (two L2 requests per warp and poll, each counter on its own line) and
-    // broadcasts; the acquire orders the ring loads of the whole warp behind it (__shfl_sync converges it)
+    // ONE lane per warp polls (two relaxed L2 loads per warp and poll, each counter on its own line) and
+    // broadcasts; the acquire fence after a successful poll orders the ring loads behind it
     auto ring_ready = [&]() {
       int ok = 1;
       if ((t & 31) == 0)
-        ok = (!need_top || ld_acquire(a.flags + (tile - 1) * kFlagStride) >= want) &&
-             (!need_bot || ld_acquire(a.flags + (tile + 1) * kFlagStride) >= want);
+        ok = (!need_top || ld_relaxed(a.flags + (tile - 1) * kFlagStride) >= want) &&
+             (!need_bot || ld_relaxed(a.flags + (tile + 1) * kFlagStride) >= want);
       return __shfl_sync(0xffffffffu, ok, 0) != 0;
     };
     auto ring_load = [&]() {
@@ -227,7 +244,10 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     };
     // at step 0 the rows are there already (written by the previous launch / the upload)
     bool have_ring = step == 0 || ring_ready();
-    if (have_ring) ring_load();
+    if (have_ring) {
+      if (step) fence_acquire_gpu();
+      ring_load();
+    }
 
     // triple of enforced values of global row gr (already clamped by the caller) at my three columns
     auto triple = [&](int gr, float (&v)[3]) {
@@ -239,41 +259,72 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         v[0] = q[ccl]; v[1] = q[ccc]; v[2] = q[ccr];
       }
     };
-    auto do_row = [&](int i) {
+    auto row_in = [&](int i, float (&nN)[3], float (&nC)[3], float (&nS)[3]) {
       const int gr = r0 + i;
-      float nN[3], nC[3], nS[3];
       triple(clampi(gr - 1, 1, H - 2), nN);
       triple(clampi(gr, 1, H - 2), nC);
       triple(clampi(gr + 1, 1, H - 2), nS);
-      const float xnew = advance(slow, i, nN, nC, nS, urow(p, i + 1)[c]);
+    };
+    auto do_row = [&](int i) {
+      float nN[3], nC[3], nS[3];
+      row_in(i, nN, nC, nS);
+      const float xnew = advance(slow, i, urow(p, i + 1)[c], nC[1], lap_row(i, nN, nC, nS));
       urow(p ^ 1, i + 1)[c] = xnew;
       return xnew;
     };
+    // rows i < j as one packed pair; row j may lie beyond the grid in the last tile (junk lane, not stored)
+    auto do_pair = [&](int i, int j) {
+      float aN[3], aC[3], aS[3], bN[3], bC[3], bS[3];
+      row_in(i, aN, aC, aS);
+      const bool jok = j < nrows;
+      if (jok) row_in(j, bN, bC, bS);
+      else {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) bN[q] = bC[q] = bS[q] = 0.f;
+      }
+      const float li = lap_row(i, aN, aC, aS), lj = jok ? lap_row(j, bN, bC, bS) : 0.f;
+      const f2 xnew = advance2(slow, i, j, f2(urow(p, i + 1)[c], jok ? urow(p, j + 1)[c] : 0.f), f2(aC[1], bC[1]),
+                               f2(li, lj));
+      urow(p ^ 1, i + 1)[c] = xnew.x;
+      if (jok) urow(p ^ 1, j + 1)[c] = xnew.y;
+      return xnew;
+    };
+    constexpr bool kPairs = MS::PACKED && MF::PACKED && TH >= 2;
 
     // interior rows: need nothing from outside the tile
     if (active) {
+      if constexpr (kPairs) {
 #pragma unroll
-      for (int i = 1; i < TH - 1; ++i)
-        if (i < nrows) do_row(i);
+        for (int i = 1; i + 1 < TH - 1; i += 2)
+          if (i < nrows) do_pair(i, i + 1);
+      } else {
+#pragma unroll
+        for (int i = 1; i < TH - 1; ++i)
+          if (i < nrows) do_row(i);
+      }
     }
     if (!have_ring) {
       unsigned spins = 0;
       while (!ring_ready()) {
         if (++spins > kSpinLimit) { *a.err = 1; break; }
-        __nanosleep(40);
+        __nanosleep(20);
       }
+      fence_acquire_gpu();
       ring_load();
     }
     // edge rows, published to the neighbours straight from registers
     if (active) {
-      const float top = do_row(0);
-      if (need_top) xg_next[(size_t)(r0 + 1) * pitch + c] = top;
-      if (TH > 1 && TH - 1 < nrows) {
-        const float bot = do_row(TH - 1);
-        if (need_bot) xg_next[(size_t)(r0 + TH - 1 + 1) * pitch + c] = bot;
-      } else if (TH == 1 && need_bot) {
-        xg_next[(size_t)(r0 + 1) * pitch + c] = top;
+      float top, bot = 0.f;
+      if constexpr (kPairs) {
+        const f2 e = do_pair(0, TH - 1);
+        top = e.x;
+        bot = e.y;
+      } else {
+        top = do_row(0);
+        if (TH > 1 && TH - 1 < nrows) bot = do_row(TH - 1);
       }
+      if (need_top) xg_next[(size_t)(r0 + 1) * pitch + c] = top;
+      if (need_bot) xg_next[(size_t)(r0 + TH - 1 + 1) * pitch + c] = TH > 1 ? bot : top;
     }
     __syncthreads();            // shared tile of the next step complete; all edge stores issued
     // release: the edge stores of all threads happen-before the barrier, the barrier before this store

@@ -30,6 +30,9 @@
 #ifndef FIB_COURT_MINB_LUT
 #define FIB_COURT_MINB_LUT 5
 #endif
+#ifndef FIB_COURT_LUT_SMEM       /* 1: stage the transposed table in shared memory (A/B, see prologue) */
+#define FIB_COURT_LUT_SMEM 0
+#endif
 #ifndef FIB_COURT_PACKED_FAST    /* two cells per thread as one f2 pair; 0 = two scalar cells (A/B) */
 #define FIB_COURT_PACKED_FAST 0
 #endif
@@ -298,7 +301,7 @@ struct Courtemanche {
     return (k == S_us) ? (US && MODE != COURT_FAST)
                        : (MODE == COURT_ALL ? true : (MODE == COURT_FAST ? is_fast(k) : !is_fast(k)));
   }
-  static size_t smem_bytes() { return 0; }
+  static size_t smem_bytes() { return (LUT && FIB_COURT_LUT_SMEM) ? sizeof(float) * kLutCols * kLutTStride : 0; }
   static const char* name() {
     static const char* n[3][2][2] = {
         {{"Courtemanche<fast>", "Courtemanche<fast,us>"}, {"Courtemanche<fast,lut>", "Courtemanche<fast,lut,us>"}},
@@ -317,7 +320,38 @@ struct Courtemanche {
                                   // on the host like the reference's Python (court.py:193-194,218)
   };
 
-  static __device__ __forceinline__ void prologue(const StepArgs<Courtemanche>&) {}
+  // Where the table lives (north_star: "lookup tables held in shared/constant memory"): measured A/B on B200
+  // (profiles/r2_tuning_log.md).  Default: the transposed copy [30][160] (19 KB) in global memory, read
+  // through L1 with ld.global.nc -- it stays L1-resident (every CTA of every wave reads the same 19 KB)
+  // and costs no shared memory, so five CTAs per SM keep all of L1.  FIB_COURT_LUT_SMEM=1 stages it into
+  // dynamic shared memory in this prologue instead (one cooperative copy + barrier per CTA).
+  static __device__ __forceinline__ void prologue(const StepArgs<Courtemanche>& a) {
+#if FIB_COURT_LUT_SMEM
+    if (LUT) {
+      extern __shared__ float fib_lut_smem[];
+      const int n = kLutCols * kLutTStride, nt = blockDim.x * blockDim.y, t = threadIdx.y * blockDim.x + threadIdx.x;
+      for (int i = t; i < n; i += nt) fib_lut_smem[i] = __ldg(a.lut + i);
+      __syncthreads();
+    }
+#else
+    (void)a;
+#endif
+  }
+  static __device__ __forceinline__ const float* lut_base(const float* global_lut) {
+#if FIB_COURT_LUT_SMEM
+    extern __shared__ float fib_lut_smem[];
+    return fib_lut_smem;
+#else
+    return global_lut;
+#endif
+  }
+  static __device__ __forceinline__ float lut_read(const float* p) {
+#if FIB_COURT_LUT_SMEM
+    return *p;
+#else
+    return __ldg(p);
+#endif
+  }
 
   // rush_larsen_b with t = tau (table flavours) or t = 1/tau (direct flavours)
   template <class T>
@@ -332,15 +366,15 @@ struct Courtemanche {
     return i < 0 ? 0 : (i >= kLutRows ? kLutRows - 1 : i);
   }
   static __device__ __forceinline__ void lut_fetch(const float* lut, float V, float (&q)[kInterCols]) {
-    const float* col = lut + lut_row(V);
+    const float* col = lut_base(lut) + lut_row(V);
 #pragma unroll
-    for (int k = 0; k < kLutCols; ++k) q[k] = __ldg(col + k * kLutTStride);
+    for (int k = 0; k < kLutCols; ++k) q[k] = lut_read(col + k * kLutTStride);
   }
   static __device__ __forceinline__ void lut_fetch(const float* lut, f2 V, f2 (&q)[kInterCols]) {
-    const float* c0 = lut + lut_row(V.x);
-    const float* c1 = lut + lut_row(V.y);
+    const float* c0 = lut_base(lut) + lut_row(V.x);
+    const float* c1 = lut_base(lut) + lut_row(V.y);
 #pragma unroll
-    for (int k = 0; k < kLutCols; ++k) q[k] = f2(__ldg(c0 + k * kLutTStride), __ldg(c1 + k * kLutTStride));
+    for (int k = 0; k < kLutCols; ++k) q[k] = f2(lut_read(c0 + k * kLutTStride), lut_read(c1 + k * kLutTStride));
   }
 
   template <class T>

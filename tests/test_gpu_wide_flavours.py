@@ -179,20 +179,19 @@ def test_lut_wide_flavour_against_the_compiled_reference_header(cuda):
         tol = 1e-5 * np.maximum(np.abs(inc[:, :, k]), 1e-3 * fl) + np.spacing(np.abs(want[:, :, k]))
         bad = np.abs(got[:, :, k].astype(np.float64) - want[:, :, k]) > tol
         assert not bad.any(), (name, int(bad.sum()), float(np.abs(got[:, :, k] - want[:, :, k]).max()))
-    # 5 steps.  The lookup truncates V to a table row and these perturbed states are far from rest (tens
-    # of mV per step), so a cell whose voltage comes within 0.1 mV of an integer at any step can read
-    # different rows in the two implementations and then diverges by whole millivolts: those cells are
-    # tracked step by step in the reference and excluded.
-    near = np.zeros(init.shape[:2], bool)
-    for n in range(1, 6):
-        vref = ref_run(n)[0][:, :, 0]
-        near |= np.abs(vref - np.round(vref)) < 0.1
-    assert near.mean() < 0.6
+    # 5 steps.  The lookup truncates V to a table row, and these perturbed states move by millivolts per
+    # step: a cell that crosses an integer voltage within the ~1e-4 mV by which two fp32 implementations
+    # differ reads different rows for one step and then diverges by whole millivolts.  With 330 000 cells a
+    # handful of such cells is certain, so the bar is on the population: at most 0.1 % of the cells off by
+    # more than 1e-3 (rel_err metric), and the typical cell within 2e-5.
     got, names, _ = cuda_run(5)
     want, _ = ref_run(5)
     for k, name in enumerate(names):
-        e = onp.rel_err(got[:, :, k][~near], want[:, :, k][~near], onp.var_floor('court_ultra', name))
-        assert e <= 1e-3, (name, e)
+        fl = onp.var_floor('court_ultra', name)
+        err = np.abs(got[:, :, k].astype(np.float64) - want[:, :, k]) / np.maximum(np.abs(want[:, :, k]), fl)
+        assert np.isfinite(err).all(), name
+        assert (err > 1e-3).mean() <= 1e-3, (name, float((err > 1e-3).mean()))
+        assert np.median(err) <= 2e-5, (name, float(np.median(err)))
 
 
 @pytest.mark.parametrize('strict', [False, True])
