@@ -140,7 +140,7 @@ struct fib_ctx {
   // persistent on-chip kernel (fib_persist.cuh): small unsharded 4v / BR grids
   int persist = -1;                   // -1 not decided yet, 0 no, 1 yes
   int persist_th = 0, persist_tiles = 0, persist_bw = 0;
-  unsigned* pflags = nullptr;         // [tiles] steps published, monotonic
+  unsigned long long* pmail = nullptr;   // edge-row mailbox of the persistent kernel, words {value, step number}
   unsigned pbase = 0;
   int* perr = nullptr;                // page-locked, device-visible: raised by a timed-out neighbour wait
   CUtensorMap pmap_x[2], pmap_s[8];
@@ -501,7 +501,7 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->red);
   cudaFree(c->ring);
   cudaFree(c->ring_count);
-  cudaFree(c->pflags);
+  cudaFree(c->pmail);
   if (c->perr) cudaFreeHost(c->perr);
   for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
   for (cudaEvent_t e : {c->ev_start, c->ev_stop, c->ev_bnd, c->ev_comm, c->ev_group})
@@ -1036,7 +1036,7 @@ static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_
   a.x[1] = c->x[1];
   a.cur = c->cur;
   a.nsteps = c->dt_per_step;
-  a.flags = c->pflags;
+  a.mail = c->pmail;
   a.base = c->pbase;
   a.err = c->perr;
   a.phase = c->phase;
@@ -1079,10 +1079,10 @@ static void decide_persist(fib_ctx* c) {
   for (int k = 0; ok && k + 1 < c->nvars; ++k) ok = make_tile_map(&c->pmap_s[k], c->s[k], c->g.W, c->g.H, P, bw, th);
   if (!ok) return;
   const int tiles = (c->g.H + th - 1) / th;
-  if (!c->pflags) {
-    const size_t fbytes = sizeof(unsigned) * (size_t)(c->sms + 2) * kFlagStride;
-    if (cudaMalloc(&c->pflags, fbytes) != cudaSuccess) { cudaGetLastError(); return; }
-    cudaMemsetAsync(c->pflags, 0, fbytes, c->stream);
+  if (!c->pmail) {
+    const size_t fbytes = sizeof(unsigned long long) * persist_mailbox_words(c->sms);
+    if (cudaMalloc(&c->pmail, fbytes) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemsetAsync(c->pmail, 0, fbytes, c->stream);       // step number 0 = "nothing published yet"
     if (cudaHostAlloc(&c->perr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
     *c->perr = 0;
   }

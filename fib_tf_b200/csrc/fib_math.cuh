@@ -59,10 +59,23 @@ struct b2 { bool x, y; };      // per-lane predicate
   }
 FIB_F2_OP3(fma2, "fma.rn.f32x2")
 FIB_F2_OP2(mul2, "mul.rn.f32x2")
-FIB_F2_OP2(add2, "add.rn.f32x2")
-FIB_F2_OP2(sub2, "sub.rn.f32x2")
 #undef FIB_F2_OP3
 #undef FIB_F2_OP2
+
+// Packed add / subtract.  ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 whatever -fmad says
+// and although the scalar mul.rn / add.rn are never fused (checked in SASS; it even sees through
+// fma(a,b,-0) and fma(p,1,b)), which would make a packed lane round differently from the scalar cell.
+// So a + b is issued as fma(a, ONE, b) with ONE = 1.0f read from constant memory at run time: exactly
+// a + b (a * 1 is exact), one FFMA2 instead of one FADD2, and nothing ptxas can fuse a multiply into.
+static __constant__ float kFibOne = 1.0f;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  const float one = kFibOne;
+  return fma2(a, f2(one), b);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  const float one = kFibOne;
+  return fma2(b, f2(-one), a);
+}
 
 __device__ __forceinline__ f2 operator+(f2 a, f2 b) { return add2(a, b); }
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { return sub2(a, b); }

@@ -14,11 +14,13 @@
 //     the start; the non-diffusing planes then live in REGISTERS (a thread owns one column of its tile)
 //     and the diffusing variable in a double-buffered shared-memory tile; TMA tile stores write
 //     everything back once at the end;
-//   * per step only the two edge rows of the diffusing variable leave the SM: each CTA stores them
-//     into the global plane (L2) and release-stores a step counter; its two neighbours acquire-poll
-//     that counter and read the rows back with L2 loads.  A step first advances the interior rows,
-//     which need nothing from outside, and only then the edge rows, so the neighbour hand-shake is
-//     hidden behind arithmetic.  One __syncthreads per step.
+//   * per step only the two edge rows of the diffusing variable leave the SM, as self-validating
+//     8-byte words {value, step number} in a small L2-resident mailbox (the "LL" protocol of NCCL): an
+//     aligned 8-byte store is one transaction, so the neighbour simply polls the words it needs until
+//     they carry the step it waits for -- no flag, no memory fence, no L1 invalidation on either side.
+//     A step first advances the interior rows, which need nothing from outside, and only then the
+//     edge rows, so the hand-shake (one L2 store + one L2 load) is hidden behind arithmetic.
+//     One __syncthreads per step (the double-buffered shared tile).
 //
 // Every cell goes through the SAME cell function and the same Laplacian / phase-term code as
 // step_kernel (fib_kernels.cuh), with the same clamped index map, and the library is built with
@@ -39,7 +41,8 @@ constexpr int kPersistThreads = 512;      // one thread per column: W <= 512
 constexpr int kPersistBox = 256;          // TMA box width (elements; the hardware limit per dimension)
 constexpr int kPersistWP = 512 + 64;      // padded row of the diffusing tile: data at +32 floats (128 B)
 constexpr unsigned kSpinLimit = 1u << 22;
-constexpr int kFlagStride = 32;           // one 128-B line per tile's step counter (no false sharing)
+// mailbox layout: [2 step parities][tiles][2 sides: 0 = top row, 1 = bottom row][kPersistThreads] words
+__host__ __device__ constexpr size_t persist_mailbox_words(int tiles) { return (size_t)2 * tiles * 2 * kPersistThreads; }
 
 // ---- PTX wrappers: mbarrier + TMA (SASS: SYNCS / UTMALDG / UTMASTG) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -79,18 +82,16 @@ __device__ __forceinline__ void tma_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
-// Polling load: relaxed at gpu scope (L2).  ld.acquire would add a CCTL.IVALL -- an invalidation of the
-// whole L1 -- to EVERY poll; instead the poll is relaxed and ONE acquire fence follows the successful one.
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// one mailbox word: {fp32 value, step number} moved as ONE aligned 8-byte transaction
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned step) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(step) : "memory");
 }
-__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void ll_load(const unsigned long long* p, float& v, unsigned& step) {
+  unsigned a, b;
+  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+  v = __uint_as_float(a);
+  step = b;
 }
-
 // ---- arguments --------------------------------------------------------------------------------
 constexpr int kPersistMaxSteps = 10;
 
@@ -106,8 +107,8 @@ struct PersistArgs {
   int cur;                     // x[cur] holds the state at the start of the launch
   int nsteps;                  // time steps of this launch (dt_per_step)
   unsigned slow_mask;          // bit s: step s is an MS step (e.g. BR n > 0), else MF (BR n == 0)
-  unsigned* flags;             // [tiles * kFlagStride] steps published so far (monotonic over the whole run)
-  unsigned base;               // value of every flag at the start of this launch
+  unsigned long long* mail;    // the mailbox (persist_mailbox_words), words {value, step number}
+  unsigned base;               // step number of the state at the start of this launch (monotonic over the run)
   int* err;                    // set to 1 if a neighbour wait ran into the spin limit
   const float* phase;          // halo layout (one row), or nullptr
   const unsigned char* pmask;  // [rows][pmask_pitch] as in StepArgs
@@ -216,23 +217,18 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
   for (int step = 0; step < a.nsteps; ++step) {
     const int p = step & 1;                                  // shared buffer holding the state at this step
     const float* xg = a.x[(a.cur + step) & 1];               // global plane with the neighbours' edge rows of it
-    float* xg_next = a.x[(a.cur + step + 1) & 1];
     const bool slow = (a.slow_mask >> step) & 1u;
-    const unsigned want = a.base + step;
+    const unsigned want = a.base + step;                     // step number of the state this step reads
     // neighbour rows (the ring): global rows r0 - 1 and r0 + TH, columns c-1, c, c+1 (clamped)
     float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
     const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
-    // ONE lane per warp polls (two relaxed L2 loads per warp and poll, each counter on its own line) and
-    // broadcasts; the acquire fence after a successful poll orders the ring loads behind it
-    auto ring_ready = [&]() {
-      int ok = 1;
-      if ((t & 31) == 0)
-        ok = (!need_top || ld_relaxed(a.flags + (tile - 1) * kFlagStride) >= want) &&
-             (!need_bot || ld_relaxed(a.flags + (tile + 1) * kFlagStride) >= want);
-      return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    // mailbox words of step number n written by `tl`'s side sd (0 = its top row, 1 = its bottom row)
+    auto box = [&](unsigned n, int tl, int sd) {
+      return a.mail + (((size_t)(n & 1u) * ntiles + tl) * 2 + sd) * kPersistThreads;
     };
-    auto ring_load = [&]() {
-      if (!active) return;
+    if (step == 0 && active) {
+      // the state at the start of a launch is complete in the global plane (previous launch / upload /
+      // stimulus), whatever the mailbox holds
       if (need_top) {
         const float* q = xg + (size_t)(r0 - 1 + 1) * pitch;
         rt[0] = __ldcg(q + ccl); rt[1] = __ldcg(q + ccc); rt[2] = __ldcg(q + ccr);
@@ -241,13 +237,30 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         const float* q = xg + (size_t)(r0 + TH + 1) * pitch;
         rb[0] = __ldcg(q + ccl); rb[1] = __ldcg(q + ccc); rb[2] = __ldcg(q + ccr);
       }
-    };
-    // at step 0 the rows are there already (written by the previous launch / the upload)
-    bool have_ring = step == 0 || ring_ready();
-    if (have_ring) {
-      if (step) fence_acquire_gpu();
-      ring_load();
     }
+    // poll my six words until they carry step number `want` (bounded: raises *err instead of hanging)
+    auto ring_wait = [&]() {
+      if (step == 0 || !active) return;
+      const int cols[3] = {ccl, ccc, ccr};
+      unsigned spins = 0;
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        if (sd == 0 ? !need_top : !need_bot) continue;
+        // the tile above publishes its BOTTOM row (side 1), the tile below its TOP row (side 0)
+        const unsigned long long* w = sd == 0 ? box(want, tile - 1, 1) : box(want, tile + 1, 0);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          float v;
+          unsigned n;
+          ll_load(w + cols[q], v, n);
+          while (n != want) {
+            if (++spins > kSpinLimit) { *a.err = 1; break; }
+            ll_load(w + cols[q], v, n);
+          }
+          if (sd == 0) rt[q] = v; else rb[q] = v;
+        }
+      }
+    };
 
     // triple of enforced values of global row gr (already clamped by the caller) at my three columns
     auto triple = [&](int gr, float (&v)[3]) {
@@ -303,15 +316,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
           if (i < nrows) do_row(i);
       }
     }
-    if (!have_ring) {
-      unsigned spins = 0;
-      while (!ring_ready()) {
-        if (++spins > kSpinLimit) { *a.err = 1; break; }
-        __nanosleep(20);
-      }
-      fence_acquire_gpu();
-      ring_load();
-    }
+    ring_wait();
     // edge rows, published to the neighbours straight from registers
     if (active) {
       float top, bot = 0.f;
@@ -323,13 +328,11 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         top = do_row(0);
         if (TH > 1 && TH - 1 < nrows) bot = do_row(TH - 1);
       }
-      if (need_top) xg_next[(size_t)(r0 + 1) * pitch + c] = top;
-      if (need_bot) xg_next[(size_t)(r0 + TH - 1 + 1) * pitch + c] = TH > 1 ? bot : top;
+      // (the last step's rows are not consumed through the mailbox: the next launch starts from the plane)
+      if (need_top) ll_store(box(want + 1, tile, 0) + c, top, want + 1);
+      if (need_bot) ll_store(box(want + 1, tile, 1) + c, TH > 1 ? bot : top, want + 1);
     }
-    __syncthreads();            // shared tile of the next step complete; all edge stores issued
-    // release: the edge stores of all threads happen-before the barrier, the barrier before this store
-    // (cumulativity); the neighbours' acquire loads then see them
-    if (t == 0) st_release(a.flags + tile * kFlagStride, want + 1);
+    __syncthreads();            // shared tile of the next step complete, the old one free for reuse
   }
 
   // ---- TMA out: registers -> staging, then tile stores (rows beyond the grid are clipped)
