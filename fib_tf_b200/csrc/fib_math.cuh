@@ -19,8 +19,9 @@
 //
 // All model code is written ONCE, generic over T = float (one cell per thread) or T = f2 (two):
 // the functions below are overloaded for both, `f2` converts implicitly from a float (broadcast), and
-// multiply-adds are spelled vfma() explicitly (the packed ops are inline PTX, which the compiler
-// never contracts; for T = float nvcc contracts a*b+c on its own).
+// multiply-adds are spelled vfma() explicitly.  Nothing else is ever fused: the library is built with
+// -fmad=false (scalar code) and the packed multiply is written so that ptxas cannot contract it (mul2
+// below), so the scalar and the packed flavour of a model round identically, cell by cell.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -58,23 +59,21 @@ struct b2 { bool x, y; };      // per-lane predicate
     return d;                                                                                           \
   }
 FIB_F2_OP3(fma2, "fma.rn.f32x2")
-FIB_F2_OP2(mul2, "mul.rn.f32x2")
+FIB_F2_OP2(add2, "add.rn.f32x2")
+FIB_F2_OP2(sub2, "sub.rn.f32x2")
 #undef FIB_F2_OP3
 #undef FIB_F2_OP2
 
-// Packed add / subtract.  ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 whatever -fmad says
-// and although the scalar mul.rn / add.rn are never fused (checked in SASS; it even sees through
-// fma(a,b,-0) and fma(p,1,b)), which would make a packed lane round differently from the scalar cell.
-// So a + b is issued as fma(a, ONE, b) with ONE = 1.0f read from constant memory at run time: exactly
-// a + b (a * 1 is exact), one FFMA2 instead of one FADD2, and nothing ptxas can fuse a multiply into.
-static __constant__ float kFibOne = 1.0f;
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  const float one = kFibOne;
-  return fma2(a, f2(one), b);
-}
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  const float one = kFibOne;
-  return fma2(b, f2(-one), a);
+// Packed multiply.  ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 whatever -fmad says,
+// although the scalar mul.rn / add.rn are never fused (checked in SASS; it even sees through
+// fma(a,b,-0) and fma(p,1,b) with literal constants), which would make a packed lane round differently
+// from the scalar cell.  So a * b is issued as fma(a, b, NZERO) with NZERO = -0.0f read from constant
+// memory at run time: exactly fl(a * b), signed zeros included (+0 + -0 = +0, -0 + -0 = -0), one FFMA2
+// instead of one FMUL2 -- and with no packed multiply left in the code there is nothing to contract.
+static __constant__ float kFibNegZero = -0.0f;
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  const float nz = kFibNegZero;
+  return fma2(a, b, f2(nz));
 }
 
 __device__ __forceinline__ f2 operator+(f2 a, f2 b) { return add2(a, b); }

@@ -138,7 +138,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
   const int c = t;
   const bool active = c < W;
   const int nblk = (W + kPersistBox - 1) / kPersistBox;
-  auto urow = [&](int p, int li) { return ub + (p * (TH + 2) + li) * kPersistWP + 32; };   // column 0 of local row li
+  auto urow = [&](int p, int li) __attribute__((always_inline)) { return ub + (p * (TH + 2) + li) * kPersistWP + 32; };   // column 0 of local row li
 
   // ---- TMA in: the diffusing tile row by row into the padded buffer, the other planes as {bw, TH} boxes
   if (t == 0) {
@@ -172,10 +172,12 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       for (int i = 0; i < TH; ++i) s[k][i] = active ? st[(k * 2 + b) * TH * kPersistBox + i * a.bw + cb] : 0.f;
   }
 
-  StepArgs<MS> sa_s;
-  StepArgs<MF> sa_f;
-  sa_s.p = a.ps;
-  sa_f.p = a.pf;
+  // the cell functions only look at `.p`: hand them the parameter blocks where they are (kernel
+  // parameter space) instead of copies
+  struct PS { const typename MS::Params& p; };
+  struct PF { const typename MF::Params& p; };
+  const PS sa_s{a.ps};
+  const PF sa_f{a.pf};
 
   // Laplacian (+ phase term) of row i: exactly step_kernel's arithmetic.  nN / nC / nS: the clamped-column
   // triples of the enforced rows above / at / below.
@@ -193,7 +195,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
   };
   // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
   // model's cell function; raw: the un-enforced centre value, x0: the enforced one
-  auto advance = [&](bool slow, int i, float raw, float x0, float lap) -> float {
+  auto advance = [&](bool slow, int i, float raw, float x0, float lap) __attribute__((always_inline)) -> float {
     float sl[NS], xnew;
 #pragma unroll
     for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
@@ -203,7 +205,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
     return xnew;
   };
-  auto advance2 = [&](bool slow, int i, int j, f2 raw, f2 x0, f2 lap) -> f2 {
+  auto advance2 = [&](bool slow, int i, int j, f2 raw, f2 x0, f2 lap) __attribute__((always_inline)) -> f2 {
     f2 sl[NS], xnew;
 #pragma unroll
     for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
@@ -223,7 +225,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
     const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
     // mailbox words of step number n written by `tl`'s side sd (0 = its top row, 1 = its bottom row)
-    auto box = [&](unsigned n, int tl, int sd) {
+    auto box = [&](unsigned n, int tl, int sd) __attribute__((always_inline)) {
       return a.mail + (((size_t)(n & 1u) * ntiles + tl) * 2 + sd) * kPersistThreads;
     };
     if (step == 0 && active) {
@@ -238,29 +240,40 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         rb[0] = __ldcg(q + ccl); rb[1] = __ldcg(q + ccc); rb[2] = __ldcg(q + ccr);
       }
     }
-    // poll my six words until they carry step number `want` (bounded: raises *err instead of hanging)
-    auto ring_wait = [&]() {
-      if (step == 0 || !active) return;
-      const int cols[3] = {ccl, ccc, ccr};
-      unsigned spins = 0;
+    // My six mailbox words (three columns on each side).  All six loads are issued back to back, so one
+    // poll costs ONE L2 round trip; the first poll is issued BEFORE the interior rows are advanced and only
+    // looked at afterwards, which hides that round trip behind arithmetic when the neighbours are on time.
+    float mv[6];
+    unsigned mn[6];
+    const int mcols[3] = {ccl, ccc, ccr};
+    auto ring_poll = [&]() __attribute__((always_inline)) {
 #pragma unroll
       for (int sd = 0; sd < 2; ++sd) {
-        if (sd == 0 ? !need_top : !need_bot) continue;
         // the tile above publishes its BOTTOM row (side 1), the tile below its TOP row (side 0)
+        const bool need = sd == 0 ? need_top : need_bot;
         const unsigned long long* w = sd == 0 ? box(want, tile - 1, 1) : box(want, tile + 1, 0);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          float v;
-          unsigned n;
-          ll_load(w + cols[q], v, n);
-          while (n != want) {
-            if (++spins > kSpinLimit) { *a.err = 1; break; }
-            ll_load(w + cols[q], v, n);
-          }
-          if (sd == 0) rt[q] = v; else rb[q] = v;
+          if (need) ll_load(w + mcols[q], mv[sd * 3 + q], mn[sd * 3 + q]);
+          else { mv[sd * 3 + q] = 0.f; mn[sd * 3 + q] = want; }
         }
       }
     };
+    auto ring_wait = [&]() __attribute__((always_inline)) {          // bounded: raises *err instead of hanging
+      if (step == 0 || !active) return;
+      unsigned spins = 0;
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ok &= mn[q] == want;
+        if (ok) break;
+        if (++spins > kSpinLimit) { *a.err = 1; break; }
+        ring_poll();
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { rt[q] = mv[q]; rb[q] = mv[3 + q]; }
+    };
+    if (step > 0 && active) ring_poll();
 
     // triple of enforced values of global row gr (already clamped by the caller) at my three columns
     auto triple = [&](int gr, float (&v)[3]) {
@@ -278,7 +291,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       triple(clampi(gr, 1, H - 2), nC);
       triple(clampi(gr + 1, 1, H - 2), nS);
     };
-    auto do_row = [&](int i) {
+    auto do_row = [&](int i) __attribute__((always_inline)) {
       float nN[3], nC[3], nS[3];
       row_in(i, nN, nC, nS);
       const float xnew = advance(slow, i, urow(p, i + 1)[c], nC[1], lap_row(i, nN, nC, nS));
@@ -286,7 +299,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       return xnew;
     };
     // rows i < j as one packed pair; row j may lie beyond the grid in the last tile (junk lane, not stored)
-    auto do_pair = [&](int i, int j) {
+    auto do_pair = [&](int i, int j) __attribute__((always_inline)) {
       float aN[3], aC[3], aS[3], bN[3], bC[3], bS[3];
       row_in(i, aN, aC, aS);
       const bool jok = j < nrows;

@@ -233,9 +233,9 @@ struct BeelerReuter {
   };
   static __device__ __forceinline__ void prologue(const StepArgs<BeelerReuter>&) {}
 
-  template <class T>
-  static __device__ __forceinline__ void cell(const StepArgs<BeelerReuter>& a, T /*raw*/, T V0, T lap,
-                                              T (&s)[NS], T& Vnew) {
+  // A: anything with a member `p` of type Params (StepArgs<BeelerReuter>, or a reference wrapper)
+  template <class A, class T>
+  static __device__ __forceinline__ void cell(const A& a, T /*raw*/, T V0, T lap, T (&s)[NS], T& Vnew) {
     const Params& p = a.p;
     const T C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
     // every current exponential is k = e^{0.04 V0} times a constant; the exact gates reuse 1/k.

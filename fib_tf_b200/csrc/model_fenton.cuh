@@ -41,9 +41,9 @@ struct Fenton4v {
   // fib_math.cuh); every operation is spelled with its own rounding (mul_rn / add_rn / vfma), so a lane of
   // the pair computes exactly what the scalar cell computes and every kernel that calls this function --
   // one step per launch, two steps per launch, the persistent kernel -- agrees bit for bit.
-  template <class T>
-  static __device__ __forceinline__ void cell(const StepArgs<Fenton4v>& a, T U, T U0, T lap, T (&s)[NS],
-                                              T& Unew) {
+  // A: anything with a member `p` of type Params (StepArgs<Fenton4v>, or a reference wrapper)
+  template <class A, class T>
+  static __device__ __forceinline__ void cell(const A& a, T U, T U0, T lap, T (&s)[NS], T& Unew) {
     constexpr float tau_vp = 3.33f, tau_vn = 19.2f, tau_wp = 160.0f, tau_wn = 75.0f;
     constexpr float tau_d = 0.065f, tau_si = 31.8364f, tau_so = 31.8364f, tau_a = 0.009f;
     constexpr float u_c = 0.23f, u_m = 1.0f, u_csi = 0.8f, u_so = 0.3f;

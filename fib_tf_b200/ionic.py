@@ -40,7 +40,7 @@ import time
 import numpy as np
 
 from . import _capi
-from .sharding import partition_rows
+from .sharding import owner_of_row, partition_rows
 
 
 class DeviceVar:
@@ -243,7 +243,7 @@ class IonicModel:
 
     def _probe(self, name, row, col):
         """One cell of a state plane; in a sharded run the owner rank reads it and shares it."""
-        own = self._row0 <= row < self._row0 + self._rows
+        own = owner_of_row(self.height, self._nranks, row) == self._rank
         v = self._ctx.probe(name, row, col) if own else None
         if self._nranks == 1:
             return v

@@ -20,7 +20,8 @@ def dump(path):
              'timeline': False, 'timeline_name': 'x', 'save_graph': False, 'skip': False, 'cheby': True}
     table = BeelerReuter(cfgbr).chebyshev_table()
     cases = [('4v', _capi.FENTON4V, 0, 1.5), ('br_exact', _capi.BR, 0, 0.809), ('br_cheby', _capi.BR, _capi.F_CHEBY, 0.809),
-             ('court_ultra', _capi.COURT_ULTRA, 0, 1.5)]
+             ('br_exact_skip', _capi.BR, _capi.F_SKIP, 0.809), ('br_cheby_skip', _capi.BR, _capi.F_CHEBY | _capi.F_SKIP, 0.809),
+             ('court', _capi.COURT, 0, 0.809), ('court_ultra', _capi.COURT_ULTRA, 0, 1.5)]
     for tag, model, flags, diff in cases:
         for d in (0.0, diff):
             c = _capi.Context(model, H, W, 0.1, d, flags=flags | _capi.F_NO_GRAPH)
@@ -36,7 +37,7 @@ def dump(path):
                     a = None
                 if a is not None:
                     c.set_state(v, a.astype(np.float32))
-            if model == _capi.COURT_ULTRA:
+            if model in (_capi.COURT, _capi.COURT_ULTRA):
                 from fib_tf_b200.court import INITIAL_STATE
                 for name, val in INITIAL_STATE:
                     if name != 'V':
@@ -45,6 +46,8 @@ def dump(path):
             if flags & _capi.F_CHEBY:
                 c.set_table(_capi.TABLE_BR_CHEBY, table)
             c.step(0, 1)
+            if model == _capi.COURT:
+                c.step(1, 1)
             out['%s/d%g/kernel' % (tag, d)] = np.array(_capi.last_kernel())
             for v in c.var_names:
                 out['%s/d%g/%s' % (tag, d, v)] = c.get_state(v)

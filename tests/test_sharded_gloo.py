@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fib_tf_b200.sharding import partition_rows
+from fib_tf_b200.sharding import halo_plan, partition_rows
 from oracle import monodomain_np as onp
 
 H, W, STEPS = 37, 29, 12
@@ -28,23 +28,25 @@ def free_port():
 
 
 def exchange(local, rank, world, halo=2):
-    """local: dict var -> [rows(+halos), W]; refresh `halo` rows per seam from the neighbours."""
+    """local: dict var -> [rows(+halos), W]; refresh `halo` rows per seam from the neighbours, following
+    the product's exchange plan (fib_tf_b200.sharding.halo_plan: peer, first row sent, first halo row
+    received, in GLOBAL rows -- the same plan the NCCL path of libfibb200 implements)."""
+    row0, rows = partition_rows(H, world)[rank]
+    lo = max(row0 - halo, 0)                       # global row of local row 0
+    plan = halo_plan(H, world, rank, depth=halo)
     for name in sorted(local):
         a = local[name]
-        top, bot = (halo if rank > 0 else 0), (halo if rank + 1 < world else 0)
-        own = a[top:a.shape[0] - bot]
-        reqs, bufs = [], {}
-        for peer, send_rows, key in ((rank - 1, own[:halo], 'top'), (rank + 1, own[-halo:], 'bot')):
-            if 0 <= peer < world:
-                bufs[key] = torch.empty(halo, W)
-                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(send_rows)), peer))
-                reqs.append(dist.irecv(bufs[key], peer))
+        reqs, recvs = [], []
+        for peer, send_row, recv_row in plan:
+            send = np.ascontiguousarray(a[send_row - lo:send_row - lo + halo])
+            buf = torch.empty(halo, W)
+            reqs.append(dist.isend(torch.from_numpy(send), peer))
+            reqs.append(dist.irecv(buf, peer))
+            recvs.append((recv_row - lo, buf))
         for r in reqs:
             r.wait()
-        if 'top' in bufs:
-            a[:halo] = bufs['top'].numpy()
-        if 'bot' in bufs:
-            a[a.shape[0] - halo:] = bufs['bot'].numpy()
+        for at, buf in recvs:
+            a[at:at + halo] = buf.numpy()
 
 
 def worker(rank, world, port, out, every=1):
