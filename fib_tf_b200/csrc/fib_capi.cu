@@ -143,6 +143,7 @@ struct fib_ctx {
   unsigned long long* pmail = nullptr;   // edge-row mailbox of the persistent kernel, words {value, step number}
   unsigned pbase = 0;
   int* perr = nullptr;                // page-locked, device-visible: raised by a timed-out neighbour wait
+  unsigned long long* ptimeline = nullptr;   // page-locked [16], FIB_PERSIST_TIMELINE=1 only
   CUtensorMap pmap_x[2], pmap_s[8];
   // NCCL
   void* comm = nullptr;
@@ -503,6 +504,7 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->ring_count);
   cudaFree(c->pmail);
   if (c->perr) cudaFreeHost(c->perr);
+  if (c->ptimeline) cudaFreeHost(c->ptimeline);
   for (int k = 0; k < 4; ++k) cudaFree(c->weights[k]);
   for (cudaEvent_t e : {c->ev_start, c->ev_stop, c->ev_bnd, c->ev_comm, c->ev_group})
     if (e) cudaEventDestroy(e);
@@ -1035,10 +1037,11 @@ static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_
   a.x[0] = c->x[0];
   a.x[1] = c->x[1];
   a.cur = c->cur;
-  a.nsteps = c->dt_per_step;
+  a.nsteps = substeps_of(c, FIB_OP_ODE);
   a.mail = c->pmail;
   a.base = c->pbase;
   a.err = c->perr;
+  a.timeline = c->ptimeline;
   a.phase = c->phase;
   a.pmask = c->pmask;
   a.pmask_pitch = c->pmask_pitch;
@@ -1074,8 +1077,8 @@ static void decide_persist(fib_ctx* c) {
   if (th > max_th) return;
   const int bw = c->g.W >= kPersistBox ? kPersistBox : (c->g.W + 3) / 4 * 4;
   const int P = c->g.pitch;
-  bool ok = make_tile_map(&c->pmap_x[0], c->x[0] + P, c->g.W, c->g.H, P, bw, 1) &&
-            make_tile_map(&c->pmap_x[1], c->x[1] + P, c->g.W, c->g.H, P, bw, 1);
+  bool ok = make_tile_map(&c->pmap_x[0], c->x[0] + P, c->g.W, c->g.H, P, bw, th) &&
+            make_tile_map(&c->pmap_x[1], c->x[1] + P, c->g.W, c->g.H, P, bw, th);
   for (int k = 0; ok && k + 1 < c->nvars; ++k) ok = make_tile_map(&c->pmap_s[k], c->s[k], c->g.W, c->g.H, P, bw, th);
   if (!ok) return;
   const int tiles = (c->g.H + th - 1) / th;
@@ -1085,6 +1088,14 @@ static void decide_persist(fib_ctx* c) {
     cudaMemsetAsync(c->pmail, 0, fbytes, c->stream);       // step number 0 = "nothing published yet"
     if (cudaHostAlloc(&c->perr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
     *c->perr = 0;
+    if (getenv("FIB_PERSIST_TIMELINE") && atoi(getenv("FIB_PERSIST_TIMELINE"))) {
+      if (cudaHostAlloc(&c->ptimeline, 16 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        c->ptimeline = nullptr;
+      } else {
+        memset(c->ptimeline, 0, 16 * sizeof(unsigned long long));
+      }
+    }
   }
   c->persist_th = th;
   c->persist_tiles = tiles;
@@ -1136,8 +1147,16 @@ static int run_iteration_persist(fib_ctx* c) {
     return 1;           // caller retries on the plain path
   }
   c->launches++;
-  c->pbase += (unsigned)c->dt_per_step;
-  if (c->dt_per_step & 1) c->cur ^= 1;
+  const int ns = substeps_of(c, FIB_OP_ODE);
+  c->pbase += (unsigned)ns;
+  if (ns & 1) c->cur ^= 1;
+  if (c->ptimeline) {          // diagnostics: print the middle tile's phase times of this launch
+    cudaStreamSynchronize(c->stream);
+    const unsigned long long* tl = c->ptimeline;
+    fprintf(stderr, "persist timeline (ns): load %llu |", tl[1] - tl[0]);
+    for (int k = 0; k < ns; ++k) fprintf(stderr, " %llu", tl[2 + k] - tl[1 + k]);
+    fprintf(stderr, " | store %llu | total %llu\n", tl[2 + ns] - tl[1 + ns], tl[2 + ns] - tl[0]);
+  }
   return 0;
 }
 

@@ -23,7 +23,8 @@ namespace fib {
 //   NEED_RAW      reaction term reads the un-enforced centre value (Fenton 4v, fenton.py:101)
 //   NEED_LAP      step needs the stencil (false for the Courtemanche 'slow' op)
 //   STORE_X       step writes the diffusing variable
-//   min_blocks(v) resident CTAs per SM the register allocator must leave room for, v cells per thread
+//   min_blocks(v, ph) resident CTAs per SM the register allocator must leave room for, v cells per thread,
+//                 ph = phase-field flavour (needs more registers)
 //   PREFETCH      prefetch the next marching row's lines into L1
 //   PACKED        with two cells per thread, run them as one f2 pair (packed fp32, fib_math.cuh)
 //   stores(k)     plane k is written by this step
@@ -69,7 +70,7 @@ inline char* last_kernel_name() {
 }
 
 template <class M, int VEC, int R, int BY, bool PHASE>
-__global__ void __launch_bounds__(kBX* BY, M::min_blocks(VEC))
+__global__ void __launch_bounds__(kBX* BY, M::min_blocks(VEC, PHASE))
 step_kernel(const Geom g, const StepArgs<M> a) {
   // Programmatic dependent launch: let the NEXT time step's kernel be scheduled while this one
   // drains (its CTAs park at their own griddepcontrol.wait), and do not touch memory before the

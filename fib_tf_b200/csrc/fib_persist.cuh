@@ -97,7 +97,7 @@ constexpr int kPersistMaxSteps = 10;
 
 template <int NS>
 struct PersistMaps {
-  CUtensorMap x[2];     // the diffusing variable's two buffers, owned rows, box {256, 1}
+  CUtensorMap x[2];     // the diffusing variable's two buffers, owned rows, box {256, TH}
   CUtensorMap s[NS];    // the other planes, box {256, TH}
 };
 
@@ -110,6 +110,8 @@ struct PersistArgs {
   unsigned long long* mail;    // the mailbox (persist_mailbox_words), words {value, step number}
   unsigned base;               // step number of the state at the start of this launch (monotonic over the run)
   int* err;                    // set to 1 if a neighbour wait ran into the spin limit
+  unsigned long long* timeline;   // optional (FIB_PERSIST_TIMELINE=1): %globaltimer of the middle tile at kernel
+                                  // start, after the TMA loads, after every step, after the TMA stores (ns)
   const float* phase;          // halo layout (one row), or nullptr
   const unsigned char* pmask;  // [rows][pmask_pitch] as in StepArgs
   int pmask_pitch;
@@ -121,55 +123,101 @@ struct PersistArgs {
 // ---- the kernel ----------------------------------------------------------------------------------
 // MS / MF: the cell types of the "slow" and "fast" steps of a schedule (Fenton4v twice; BeelerReuter<C,true>
 // and <C,false> for br.py's skip schedule).  TH: rows per tile.  PHASE: phase field present.
+//
+// Where the state lives between the steps of a launch:
+//   * a thread owns ONE column of its tile: its TH cells of every plane, the diffusing variable included
+//     (the raw values), stay in registers;
+//   * shared memory holds the ENFORCED diffusing field of the tile plus a one-cell ring, i.e. what the
+//     stencil of fib_stencil.cuh reads, Xp[r][c] = X[clamp(r,1,H-2)][clamp(c,1,W-2)], materialised:
+//     local row li <-> global row r0 + li - 1, column c at offset 32 + c (columns -1 and W included).
+//     Away from the grid's border that is the field itself; on the border the writers duplicate the
+//     neighbouring interior value into the ring positions.  Every stencil read is then a plain
+//     [li + dr][c + dc] shared-memory load with static offsets -- no clamping, no branches per cell --
+//     and the rows of a column are read once per step (marching reuse in registers);
+//   * the rows of the neighbour tiles arrive through the mailbox and are written into the ring rows by
+//     the thread that will read them (each thread writes the three columns it reads: no barrier).
 template <class MS, class MF, int TH, bool PHASE>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, const PersistArgs<MS, MF> a) {
   constexpr int NS = MS::NS;
   static_assert(MS::NS == MF::NS, "slow / fast steps share the state layout");
+  static_assert(TH >= 2, "tiles are at least two rows high");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* ub = reinterpret_cast<float*>(smem_raw);                         // [2][TH + 2][kPersistWP]
-  float* st = ub + 2 * (TH + 2) * kPersistWP;                             // [NS][2 column blocks][TH rows of bw][.. 256]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(st + NS * TH * 512);
+  float* ub = reinterpret_cast<float*>(smem_raw);                 // [2][TH + 2][kPersistWP] enforced field + ring
+  float* st = ub + 2 * (TH + 2) * kPersistWP;                     // [NS + 1][2 column blocks][TH][256] TMA staging
+  uint64_t* bar = reinterpret_cast<uint64_t*>(st + (NS + 1) * TH * 512);
 
   const int t = threadIdx.x, tile = blockIdx.x, ntiles = gridDim.x;
+  const bool stamp = a.timeline && t == 0 && tile == ntiles / 2;
+  auto now = [&](int slot) __attribute__((always_inline)) {
+    if (stamp) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+      a.timeline[slot] = ns;
+    }
+  };
+  now(0);
   const int W = g.W, H = g.H, pitch = g.pitch;
   const int r0 = tile * TH;
   const int nrows = min(TH, H - r0);
   const int c = t;
   const bool active = c < W;
   const int nblk = (W + kPersistBox - 1) / kPersistBox;
-  auto urow = [&](int p, int li) __attribute__((always_inline)) { return ub + (p * (TH + 2) + li) * kPersistWP + 32; };   // column 0 of local row li
+  // column 0 of local row li of buffer p
+  auto urow = [&](int p, int li) __attribute__((always_inline)) { return ub + (p * (TH + 2) + li) * kPersistWP + 32; };
+  auto stage = [&](int k, int b) __attribute__((always_inline)) { return st + (k * 2 + b) * TH * kPersistBox; };
 
-  // ---- TMA in: the diffusing tile row by row into the padded buffer, the other planes as {bw, TH} boxes
+  // ---- TMA in: every plane of the tile as {bw, TH} boxes (plane NS = the diffusing variable)
   if (t == 0) {
     mbar_init(bar, 1);
     fence_async_smem();
   }
   __syncthreads();
   if (t == 0) {
-    mbar_expect_tx(bar, (uint32_t)((TH + NS * TH) * nblk * a.bw * sizeof(float)));
+    mbar_expect_tx(bar, (uint32_t)((NS + 1) * TH * nblk * a.bw * sizeof(float)));
     for (int b = 0; b < nblk; ++b) {
-      for (int i = 0; i < TH; ++i) tma_load_2d(urow(0, i + 1) + b * kPersistBox, &maps.x[a.cur], b * kPersistBox, r0 + i, bar);
-      for (int k = 0; k < NS; ++k) tma_load_2d(st + (k * 2 + b) * TH * kPersistBox, &maps.s[k], b * kPersistBox, r0, bar);
+      tma_load_2d(stage(NS, b), a.cur ? &maps.x[1] : &maps.x[0], b * kPersistBox, r0, bar);
+      for (int k = 0; k < NS; ++k) tma_load_2d(stage(k, b), &maps.s[k], b * kPersistBox, r0, bar);
     }
   }
-  // meanwhile: which of my cells have a non-trivial phase term (same flags as step_kernel)
+  // meanwhile: which of my cells have a non-trivial phase term (same flags as step_kernel) ...
   unsigned phbits = 0;
   if (PHASE && active) {
 #pragma unroll
     for (int i = 0; i < TH; ++i)
       if (i < nrows && a.pmask[(r0 + i) * a.pmask_pitch + (c >> 5)]) phbits |= 1u << i;
   }
+  // ... the columns I write (the enforced field duplicates column 1 into 0 and -1, W-2 into W-1 and W) ...
   const int ccl = clampi(c - 1, 1, W - 2), ccc = clampi(c, 1, W - 2), ccr = clampi(c + 1, 1, W - 2);
+  const bool wr_own = active && c >= 1 && c <= W - 2, wr_lo = c == 1, wr_hi = c == W - 2;
+  auto put = [&](float* row, float v) __attribute__((always_inline)) {
+    if (wr_own) row[c] = v;
+    if (wr_lo) { row[0] = v; row[-1] = v; }
+    if (wr_hi) { row[W - 1] = v; row[W] = v; }
+  };
+  // ... and which global row local row li shows: src[li] = local index of row clamp(r0 + li - 1, 1, H - 2)
+  // (0 = the row above the tile, 1..TH = my rows, TH + 1 = the row below); identity except at the grid's border
+  int src[TH + 2];
+  bool plain_tile = true;
+#pragma unroll
+  for (int li = 0; li < TH + 2; ++li) {
+    const int gr = r0 + li - 1;
+    src[li] = (gr >= -1 && gr <= H) ? clampi(gr, 1, H - 2) - r0 + 1 : -1;
+    if (src[li] != li && src[li] >= 0) plain_tile = false;
+  }
+  const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
   while (!mbar_try_wait(bar, 0)) {}
+  now(1);
 
-  float s[NS][TH];
+  float s[NS][TH], u[TH];
   {
     const int b = c / kPersistBox, cb = c - b * kPersistBox;
 #pragma unroll
-    for (int k = 0; k < NS; ++k)
+    for (int i = 0; i < TH; ++i) {
 #pragma unroll
-      for (int i = 0; i < TH; ++i) s[k][i] = active ? st[(k * 2 + b) * TH * kPersistBox + i * a.bw + cb] : 0.f;
+      for (int k = 0; k < NS; ++k) s[k][i] = active ? stage(k, b)[i * a.bw + cb] : 0.f;
+      u[i] = active ? stage(NS, b)[i * a.bw + cb] : 0.f;
+    }
   }
 
   // the cell functions only look at `.p`: hand them the parameter blocks where they are (kernel
@@ -179,67 +227,59 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
   const PS sa_s{a.ps};
   const PF sa_f{a.pf};
 
-  // Laplacian (+ phase term) of row i: exactly step_kernel's arithmetic.  nN / nC / nS: the clamped-column
-  // triples of the enforced rows above / at / below.
-  auto lap_row = [&](int i, const float (&nN)[3], const float (&nC)[3], const float (&nS)[3]) -> float {
-    float lap = lap9(nN[1], nS[1], nC[0], nC[2], nN[0], nS[0], nN[2], nS[2], nC[1]);
-    if (PHASE && ((phbits >> i) & 1u)) {
-      const int gr = r0 + i;
-      const float* ph = a.phase;
-      const int rN = (reflecti(gr - 1, H) + 1) * pitch, rC = (gr + 1) * pitch, rS = (reflecti(gr + 1, H) + 1) * pitch;
-      const float pN = ph[rN + c], pS = ph[rS + c];
-      const float pW = ph[rC + clampi(reflecti(c - 1, W), 0, W - 1)], pE = ph[rC + clampi(reflecti(c + 1, W), 0, W - 1)];
-      lap = __fadd_rn(lap, phase_term(nN[1], nS[1], nC[0], nC[2], pN, pS, pW, pE, ph[rC + c]));
+  // rows of the enforced field that show one of MY rows: written from registers (`vals` = my TH values)
+  auto write_own = [&](int p, const float (&vals)[TH], int first, int last) __attribute__((always_inline)) {
+    if (plain_tile) {
+#pragma unroll
+      for (int i = 0; i < TH; ++i)
+        if (i >= first && i <= last && i < nrows) put(urow(p, i + 1), vals[i]);
+    } else {                      // a tile on the grid's border: some rows show a neighbouring row
+#pragma unroll
+      for (int li = 0; li < TH + 2; ++li)
+#pragma unroll
+        for (int i = 0; i < TH; ++i)
+          if (src[li] == i + 1 && i >= first && i <= last) put(urow(p, li), vals[i]);
     }
-    return lap;
   };
-  // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
-  // model's cell function; raw: the un-enforced centre value, x0: the enforced one
-  auto advance = [&](bool slow, int i, float raw, float x0, float lap) __attribute__((always_inline)) -> float {
-    float sl[NS], xnew;
+  // rows that show a NEIGHBOUR tile's row: each thread writes the three columns it will read itself
+  // (the mailbox / plane loads used clamped columns, so these are enforced values already)
+  auto write_ring = [&](int p, const float (&rt)[3], const float (&rb)[3]) __attribute__((always_inline)) {
+    if (!active) return;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
-    if (slow) MS::cell(sa_s, raw, x0, lap, sl, xnew);
-    else MF::cell(sa_f, raw, x0, lap, sl, xnew);
-#pragma unroll
-    for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
-    return xnew;
+    for (int li = 0; li < TH + 2; ++li) {
+      if (src[li] == 0) { float* q = urow(p, li) + c; q[-1] = rt[0]; q[0] = rt[1]; q[1] = rt[2]; }
+      if (src[li] == TH + 1) { float* q = urow(p, li) + c; q[-1] = rb[0]; q[0] = rb[1]; q[1] = rb[2]; }
+    }
   };
-  auto advance2 = [&](bool slow, int i, int j, f2 raw, f2 x0, f2 lap) __attribute__((always_inline)) -> f2 {
-    f2 sl[NS], xnew;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
-    if (slow) MS::cell(sa_s, raw, x0, lap, sl, xnew);
-    else MF::cell(sa_f, raw, x0, lap, sl, xnew);
-#pragma unroll
-    for (int k = 0; k < NS; ++k) { s[k][i] = sl[k].x; s[k][j] = sl[k].y; }
-    return xnew;
+
+  // ---- step 0 input: my rows from registers, the neighbours' rows from the global plane (complete at the
+  // start of a launch: previous launch / upload / stimulus -- whatever the mailbox holds)
+  {
+    const float* xg = a.cur ? a.x[1] : a.x[0];
+    float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
+    if (active && need_top) {
+      const float* q = xg + (size_t)(r0 - 1 + 1) * pitch;
+      rt[0] = __ldcg(q + ccl); rt[1] = __ldcg(q + ccc); rt[2] = __ldcg(q + ccr);
+    }
+    if (active && need_bot) {
+      const float* q = xg + (size_t)(r0 + TH + 1) * pitch;
+      rb[0] = __ldcg(q + ccl); rb[1] = __ldcg(q + ccc); rb[2] = __ldcg(q + ccr);
+    }
+    write_own(0, u, 0, TH - 1);
+    __syncthreads();              // (the ring rows may overlap rows written above on border tiles: order them)
+    write_ring(0, rt, rb);
+    __syncthreads();
+  }
+
+  // mailbox words of step number n written by `tl`'s side sd (0 = its top row, 1 = its bottom row)
+  auto box = [&](unsigned n, int tl, int sd) __attribute__((always_inline)) {
+    return a.mail + (((size_t)(n & 1u) * ntiles + tl) * 2 + sd) * kPersistThreads;
   };
 
   for (int step = 0; step < a.nsteps; ++step) {
-    const int p = step & 1;                                  // shared buffer holding the state at this step
-    const float* xg = a.x[(a.cur + step) & 1];               // global plane with the neighbours' edge rows of it
+    const int p = step & 1;                                  // shared buffer holding the state this step reads
     const bool slow = (a.slow_mask >> step) & 1u;
-    const unsigned want = a.base + step;                     // step number of the state this step reads
-    // neighbour rows (the ring): global rows r0 - 1 and r0 + TH, columns c-1, c, c+1 (clamped)
-    float rt[3] = {0.f, 0.f, 0.f}, rb[3] = {0.f, 0.f, 0.f};
-    const bool need_top = tile > 0, need_bot = tile + 1 < ntiles;
-    // mailbox words of step number n written by `tl`'s side sd (0 = its top row, 1 = its bottom row)
-    auto box = [&](unsigned n, int tl, int sd) __attribute__((always_inline)) {
-      return a.mail + (((size_t)(n & 1u) * ntiles + tl) * 2 + sd) * kPersistThreads;
-    };
-    if (step == 0 && active) {
-      // the state at the start of a launch is complete in the global plane (previous launch / upload /
-      // stimulus), whatever the mailbox holds
-      if (need_top) {
-        const float* q = xg + (size_t)(r0 - 1 + 1) * pitch;
-        rt[0] = __ldcg(q + ccl); rt[1] = __ldcg(q + ccc); rt[2] = __ldcg(q + ccr);
-      }
-      if (need_bot) {
-        const float* q = xg + (size_t)(r0 + TH + 1) * pitch;
-        rb[0] = __ldcg(q + ccl); rb[1] = __ldcg(q + ccc); rb[2] = __ldcg(q + ccr);
-      }
-    }
+    const unsigned want = a.base + step;                     // step number of that state
     // My six mailbox words (three columns on each side).  All six loads are issued back to back, so one
     // poll costs ONE L2 round trip; the first poll is issued BEFORE the interior rows are advanced and only
     // looked at afterwards, which hides that round trip behind arithmetic when the neighbours are on time.
@@ -259,66 +299,59 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         }
       }
     };
-    auto ring_wait = [&]() __attribute__((always_inline)) {          // bounded: raises *err instead of hanging
-      if (step == 0 || !active) return;
-      unsigned spins = 0;
-      for (;;) {
-        bool ok = true;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) ok &= mn[q] == want;
-        if (ok) break;
-        if (++spins > kSpinLimit) { *a.err = 1; break; }
-        ring_poll();
-      }
-#pragma unroll
-      for (int q = 0; q < 3; ++q) { rt[q] = mv[q]; rb[q] = mv[3 + q]; }
-    };
     if (step > 0 && active) ring_poll();
 
-    // triple of enforced values of global row gr (already clamped by the caller) at my three columns
-    auto triple = [&](int gr, float (&v)[3]) {
-      const int li = gr - r0 + 1;
-      if (li == 0) { v[0] = rt[0]; v[1] = rt[1]; v[2] = rt[2]; }
-      else if (li == TH + 1) { v[0] = rb[0]; v[1] = rb[1]; v[2] = rb[2]; }
-      else {
-        const float* q = urow(p, li);
-        v[0] = q[ccl]; v[1] = q[ccc]; v[2] = q[ccr];
+    // the three enforced values around my column in local row li
+    float T[TH + 2][3];
+    auto load_row = [&](int li) __attribute__((always_inline)) {
+      const float* q = urow(p, li) + c;
+      T[li][0] = q[-1]; T[li][1] = q[0]; T[li][2] = q[1];
+    };
+    // Laplacian (+ phase term) of my row i: exactly step_kernel's arithmetic on the same values
+    auto lap_row = [&](int i) __attribute__((always_inline)) -> float {
+      float lap = lap9(T[i][1], T[i + 2][1], T[i + 1][0], T[i + 1][2], T[i][0], T[i + 2][0], T[i][2], T[i + 2][2],
+                       T[i + 1][1]);
+      if (PHASE && ((phbits >> i) & 1u)) {
+        const int gr = r0 + i;
+        const float* ph = a.phase;
+        const int rN = (reflecti(gr - 1, H) + 1) * pitch, rC = (gr + 1) * pitch, rS = (reflecti(gr + 1, H) + 1) * pitch;
+        const float pN = ph[rN + c], pS = ph[rS + c];
+        const float pW = ph[rC + clampi(reflecti(c - 1, W), 0, W - 1)], pE = ph[rC + clampi(reflecti(c + 1, W), 0, W - 1)];
+        lap = __fadd_rn(lap, phase_term(T[i][1], T[i + 2][1], T[i + 1][0], T[i + 1][2], pN, pS, pW, pE, ph[rC + c]));
       }
+      return lap;
     };
-    auto row_in = [&](int i, float (&nN)[3], float (&nC)[3], float (&nS)[3]) {
-      const int gr = r0 + i;
-      triple(clampi(gr - 1, 1, H - 2), nN);
-      triple(clampi(gr, 1, H - 2), nC);
-      triple(clampi(gr + 1, 1, H - 2), nS);
-    };
+    // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
+    // model's cell function; u[]: the raw centre values, T[.][1]: the enforced ones
     auto do_row = [&](int i) __attribute__((always_inline)) {
-      float nN[3], nC[3], nS[3];
-      row_in(i, nN, nC, nS);
-      const float xnew = advance(slow, i, urow(p, i + 1)[c], nC[1], lap_row(i, nN, nC, nS));
-      urow(p ^ 1, i + 1)[c] = xnew;
-      return xnew;
-    };
-    // rows i < j as one packed pair; row j may lie beyond the grid in the last tile (junk lane, not stored)
-    auto do_pair = [&](int i, int j) __attribute__((always_inline)) {
-      float aN[3], aC[3], aS[3], bN[3], bC[3], bS[3];
-      row_in(i, aN, aC, aS);
-      const bool jok = j < nrows;
-      if (jok) row_in(j, bN, bC, bS);
-      else {
+      float sl[NS], xnew;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) bN[q] = bC[q] = bS[q] = 0.f;
-      }
-      const float li = lap_row(i, aN, aC, aS), lj = jok ? lap_row(j, bN, bC, bS) : 0.f;
-      const f2 xnew = advance2(slow, i, j, f2(urow(p, i + 1)[c], jok ? urow(p, j + 1)[c] : 0.f), f2(aC[1], bC[1]),
-                               f2(li, lj));
-      urow(p ^ 1, i + 1)[c] = xnew.x;
-      if (jok) urow(p ^ 1, j + 1)[c] = xnew.y;
-      return xnew;
+      for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
+      const float lap = lap_row(i);
+      if (slow) MS::cell(sa_s, u[i], T[i + 1][1], lap, sl, xnew);
+      else MF::cell(sa_f, u[i], T[i + 1][1], lap, sl, xnew);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
+      u[i] = xnew;
     };
-    constexpr bool kPairs = MS::PACKED && MF::PACKED && TH >= 2;
+    auto do_pair = [&](int i, int j) __attribute__((always_inline)) {      // j >= nrows: junk lane, never stored
+      f2 sl[NS], xnew;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
+      const f2 lap(lap_row(i), lap_row(j));
+      if (slow) MS::cell(sa_s, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
+      else MF::cell(sa_f, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) { s[k][i] = sl[k].x; s[k][j] = sl[k].y; }
+      u[i] = xnew.x;
+      u[j] = xnew.y;
+    };
+    constexpr bool kPairs = MS::PACKED && MF::PACKED;
 
     // interior rows: need nothing from outside the tile
     if (active) {
+#pragma unroll
+      for (int li = 1; li <= TH; ++li) load_row(li);
       if constexpr (kPairs) {
 #pragma unroll
         for (int i = 1; i + 1 < TH - 1; i += 2)
@@ -329,50 +362,71 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
           if (i < nrows) do_row(i);
       }
     }
-    ring_wait();
+    // the neighbours' rows of this step: wait for the mailbox (bounded: raises *err instead of hanging),
+    // put them where my stencil reads them
+    if (step > 0 && active) {
+      unsigned spins = 0;
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ok &= mn[q] == want;
+        if (ok) break;
+        if (++spins > kSpinLimit) { *a.err = 1; break; }
+        ring_poll();
+      }
+      const float rt[3] = {mv[0], mv[1], mv[2]}, rb[3] = {mv[3], mv[4], mv[5]};
+      write_ring(p, rt, rb);
+    }
     // edge rows, published to the neighbours straight from registers
     if (active) {
-      float top, bot = 0.f;
+      load_row(0);
+      load_row(TH + 1);
+      if (!plain_tile) {          // border tiles: the ring write may have refreshed rows loaded earlier
+#pragma unroll
+        for (int li = 1; li <= TH; ++li) load_row(li);
+      }
       if constexpr (kPairs) {
-        const f2 e = do_pair(0, TH - 1);
-        top = e.x;
-        bot = e.y;
+        do_pair(0, TH - 1);
       } else {
-        top = do_row(0);
-        if (TH > 1 && TH - 1 < nrows) bot = do_row(TH - 1);
+        do_row(0);
+        if (TH - 1 < nrows) do_row(TH - 1);
       }
       // (the last step's rows are not consumed through the mailbox: the next launch starts from the plane)
-      if (need_top) ll_store(box(want + 1, tile, 0) + c, top, want + 1);
-      if (need_bot) ll_store(box(want + 1, tile, 1) + c, TH > 1 ? bot : top, want + 1);
+      if (need_top) ll_store(box(want + 1, tile, 0) + c, u[0], want + 1);
+      if (need_bot) ll_store(box(want + 1, tile, 1) + c, u[TH - 1], want + 1);
+      write_own(p ^ 1, u, 0, TH - 1);
     }
     __syncthreads();            // shared tile of the next step complete, the old one free for reuse
+    now(2 + step);
   }
 
   // ---- TMA out: registers -> staging, then tile stores (rows beyond the grid are clipped)
   if (active) {
     const int b = c / kPersistBox, cb = c - b * kPersistBox;
 #pragma unroll
-    for (int k = 0; k < NS; ++k)
+    for (int i = 0; i < TH; ++i) {
 #pragma unroll
-      for (int i = 0; i < TH; ++i) st[(k * 2 + b) * TH * kPersistBox + i * a.bw + cb] = s[k][i];
+      for (int k = 0; k < NS; ++k) stage(k, b)[i * a.bw + cb] = s[k][i];
+      stage(NS, b)[i * a.bw + cb] = u[i];
+    }
   }
   fence_async_smem();
   __syncthreads();
   if (t == 0) {
-    const int pf = a.nsteps & 1;
-    const CUtensorMap* mx = &maps.x[(a.cur + a.nsteps) & 1];
+    const CUtensorMap* mx = ((a.cur + a.nsteps) & 1) ? &maps.x[1] : &maps.x[0];
     for (int b = 0; b < nblk; ++b) {
-      for (int i = 0; i < TH; ++i) tma_store_2d(mx, b * kPersistBox, r0 + i, urow(pf, i + 1) + b * kPersistBox);
+      tma_store_2d(mx, b * kPersistBox, r0, stage(NS, b));
       for (int k = 0; k < NS; ++k)
-        if (MS::stores(k) || MF::stores(k)) tma_store_2d(&maps.s[k], b * kPersistBox, r0, st + (k * 2 + b) * TH * kPersistBox);
+        if (MS::stores(k) || MF::stores(k)) tma_store_2d(&maps.s[k], b * kPersistBox, r0, stage(k, b));
     }
     tma_store_commit_wait();
   }
+  now(2 + a.nsteps);
 }
 
 template <int NS, int TH>
 constexpr size_t persist_smem_bytes() {
-  return (size_t)(2 * (TH + 2) * kPersistWP + NS * TH * 512) * sizeof(float) + 64;
+  return (size_t)(2 * (TH + 2) * kPersistWP + (NS + 1) * TH * 512) * sizeof(float) + 64;
 }
 
 }  // namespace fib

@@ -208,7 +208,7 @@ struct BeelerReuter {
   static constexpr int MIN_BLOCKS =
       SLOW ? (CHEBY == 1 ? FIB_BR_MINB_SLOW : FIB_BR_MINB_SLOW_EXACT) : FIB_BR_MINB_FAST;
   // the one-cell-per-thread flavour of small grids keeps 6 (512^2 + hole: 45.7 vs 44.2 at 7)
-  static __host__ __device__ constexpr int min_blocks(int vec) {
+  static __host__ __device__ constexpr int min_blocks(int vec, bool /*phase*/) {
     return (SLOW && CHEBY == 1 && vec == 1) ? 6 : MIN_BLOCKS;
   }
   static constexpr bool PREFETCH = true;

@@ -123,7 +123,7 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
   }
 #endif
 
-  q[Q_d_inf] = m_rcp(1.0f + m_exp((V + 10.0f) * -0.125f));
+  q[Q_d_inf] = m_rcp(m_exp_affine((V + 10.0f) * -0.125f, 1.f, 1.0f));
   {
     const T e = ey[0], one_m_e = -em1[0];
     T t = RATES ? m_div((wd * 0.0350000f) * (1.0f + e), one_m_e) : m_div(one_m_e, (wd * 0.0350000f) * (1.0f + e));
@@ -152,7 +152,7 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     t = sel(lt(vabs(ww), T(1.0e-10f)), T(RATES ? (float)(1.3 / (6.0 * 0.2)) : (float)((6.0 * 0.2) / 1.3)), t);
     q[Q_tau_w] = t;
   }
-  q[Q_w_inf] = 1.0f - m_rcp(1.0f + m_exp((V - 40.0f) * -FIB_RCPF(17.0)));
+  q[Q_w_inf] = 1.0f - m_rcp(m_exp_affine((V - 40.0f) * -FIB_RCPF(17.0), 1.f, 1.0f));
   {
     const T w = V + 47.13f;
     const T alpha_m = sel(lt(vabs(V - -47.13f), T(0.001f)), T(3.2f), m_div(w * 0.32f, 1.0f - m_exp(w * -0.1f)));
@@ -177,9 +177,9 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     // alpha_j = aN/aD, beta_j = bN/bD
     const T aN = sel(lo, vfma(T(-127140.f), m_exp(V * 0.2444f), m_exp(V * -0.04391f) * -3.474e-05f) * (V + 37.78f),
                      eps);
-    const T aD = sel(lo, 1.0f + m_exp((V + 79.23f) * 0.311f), T(1.0f));
+    const T aD = sel(lo, m_exp_affine((V + 79.23f) * 0.311f, 1.f, 1.0f), T(1.0f));
     const T bN = m_exp(sel(lo, V * -0.01052f, V * -2.535e-07f)) * sel(lo, T(0.1212f), T(0.3f));
-    const T bD = 1.0f + m_exp(sel(lo, (V + 40.14f) * -0.1378f, (V + 32.0f) * -0.1f));
+    const T bD = m_exp_affine(sel(lo, (V + 40.14f) * -0.1378f, (V + 32.0f) * -0.1f), 1.f, 1.0f);
     if (RATES) {        // over the common denominator: one reciprocal each for inf and rate
       const T x = aN * bD;
       const T t = vfma(bN, aD, x);
@@ -197,7 +197,7 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
   {
     // alpha/beta of oa and ua are the same expressions (court.py:363-364, 375-376)
     const T x = m_exp(Vs * -FIB_RCPF(8.5)) + m_exp((Vs - 40.0f) * -FIB_RCPF(59.0));
-    const T y2 = 2.5f + m_exp((Vs + 72.0f) * FIB_RCPF(17.0));
+    const T y2 = m_exp_affine((Vs + 72.0f) * FIB_RCPF(17.0), 1.f, 2.5f);
     T t;
     if (RATES) {      // K_Q10 (0.65/x + 0.65/y) = 1.95 (x + y)/(x y)
       t = ((x + y2) * (float)(3.0 * 0.65)) * m_rcp(x * y2);
@@ -209,21 +209,21 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     q[Q_tau_oa] = t;
     q[Q_tau_ua] = t;
   }
-  q[Q_oa_inf] = m_rcp(1.0f + m_exp((Vs + 10.47f) * -FIB_RCPF(17.54)));
+  q[Q_oa_inf] = m_rcp(m_exp_affine((Vs + 10.47f) * -FIB_RCPF(17.54), 1.f, 1.0f));
   {
-    const T x = 18.53f + m_exp((Vs + 103.7f) * FIB_RCPF(10.95));
-    const T y2 = 35.56f + m_exp((Vs - 8.74f) * -FIB_RCPF(7.44));
+    const T x = m_exp_affine((Vs + 103.7f) * FIB_RCPF(10.95), 1.f, 18.53f);
+    const T y2 = m_exp_affine((Vs - 8.74f) * -FIB_RCPF(7.44), 1.f, 35.56f);
     if (RATES) q[Q_tau_oi] = ((x + y2) * 3.0f) * m_rcp(x * y2);
     else q[Q_tau_oi] = m_rcp(m_rcp(x) + m_rcp(y2)) * FIB_RCPF(3.0);
   }
-  q[Q_oi_inf] = m_rcp(1.0f + m_exp((Vs + 33.1f) * FIB_RCPF(5.3)));
-  q[Q_ua_inf] = m_rcp(1.0f + m_exp((Vs + 20.3f) * -FIB_RCPF(9.6)));
+  q[Q_oi_inf] = m_rcp(m_exp_affine((Vs + 33.1f) * FIB_RCPF(5.3), 1.f, 1.0f));
+  q[Q_ua_inf] = m_rcp(m_exp_affine((Vs + 20.3f) * -FIB_RCPF(9.6), 1.f, 1.0f));
   {
-    const T alpha = m_rcp(21.0f + m_exp((Vs - 195.000f) * -FIB_RCPF(28.0)));
+    const T alpha = m_rcp(m_exp_affine((Vs - 195.000f) * -FIB_RCPF(28.0), 1.f, 21.0f));
     const T beta = m_exp((Vs - 168.0f) * 0.0625f);          // 1 / e^{-z} = e^{z}
     q[Q_tau_ui] = RATES ? (alpha + beta) * 3.0f : m_rcp(alpha + beta) * FIB_RCPF(3.0);
   }
-  q[Q_ui_inf] = m_rcp(1.0f + m_exp((Vs - 109.45f) * FIB_RCPF(27.48)));
+  q[Q_ui_inf] = m_rcp(m_exp_affine((Vs - 109.45f) * FIB_RCPF(27.48), 1.f, 1.0f));
   {
     const auto sw = lt(vabs(wr), T(1.0e-10f)), sz = lt(vabs(zr), T(1.0e-10f));
     const T aN = sel(sw, T(0.0015f), wr * 0.0003f), aD = sel(sw, T(1.0f), -em1[2]);    // 1 - e^{-0.2 w}
@@ -231,7 +231,7 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     const T bD = sel(sz, T(1.0f), em1[3]);                                       // e^{z/5.1237} - 1
     if (RATES) q[Q_tau_xr] = vfma(aN, bD, bN * aD) * m_rcp(aD * bD);
     else q[Q_tau_xr] = m_rcp(m_div(aN, aD) + m_div(bN, bD));
-    q[Q_xr_inf] = m_rcp(1.0f + m_exp(wr * -FIB_RCPF(6.5)));
+    q[Q_xr_inf] = m_rcp(m_exp_affine(wr * -FIB_RCPF(6.5), 1.f, 1.0f));
   }
   {
     const auto z0 = lt(vabs(ws), T(1.0e-10f));
@@ -239,9 +239,9 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     const T bN = sel(z0, T(0.000315f), ws * 3.5e-05f), bD = sel(z0, T(1.0f), em1[5]);    // e^{w/9} - 1
     if (RATES) q[Q_tau_xs] = (vfma(aN, bD, bN * aD) * 2.0f) * m_rcp(aD * bD);
     else q[Q_tau_xs] = m_rcp(m_div(aN, aD) + m_div(bN, bD)) * 0.5f;
-    q[Q_xs_inf] = m_sqrt(m_rcp(1.0f + m_exp(ws * -FIB_RCPF(12.7))));
+    q[Q_xs_inf] = m_sqrt(m_rcp(m_exp_affine(ws * -FIB_RCPF(12.7), 1.f, 1.0f)));
   }
-  q[Q_g_Kur] = vfma(T(0.05f), m_rcp(1.0f + m_exp((V - 15.0f) * -FIB_RCPF(13.0))), T(0.005f));
+  q[Q_g_Kur] = vfma(T(0.05f), m_rcp(m_exp_affine((V - 15.0f) * -FIB_RCPF(13.0), 1.f, 1.0f)), T(0.005f));
   {
     constexpr float rRT = FIB_RCPF(R * T_K);
     q[Q_f_NaK] = m_rcp(vfma(T((float)(0.0365 * sigma)), m_exp((V * (float)(-F)) * rRT),
@@ -253,8 +253,8 @@ __device__ __forceinline__ void court_inter_dev(T V, T (&q)[kInterCols]) {
     // e^{(gamma-1) F V / RT} is eg1 again (court.py:421 vs :417 differ only in operand order)
     q[Q_i_NaCab] = ((eg1 * (float)(Na_o * Na_o * Na_o)) * (float)(Cm * I_NaCa_max)) * rd;
   }
-  q[Q_i_K1a] = m_rcp(1.0f + m_exp((V + 80.0f) * 0.07f)) * (float)(Cm * g_K1);
-  q[Q_i_Kra] = m_rcp(1.0f + m_exp((V + 15.0f) * FIB_RCPF(22.4))) * (float)(Cm * g_Kr);
+  q[Q_i_K1a] = m_rcp(m_exp_affine((V + 80.0f) * 0.07f, 1.f, 1.0f)) * (float)(Cm * g_K1);
+  q[Q_i_Kra] = m_rcp(m_exp_affine((V + 15.0f) * FIB_RCPF(22.4), 1.f, 1.0f)) * (float)(Cm * g_Kr);
   if (WANT_US) {   // court_ultra.py:445-450
     const T a_us = map_lanes(V, [](float v) { return 3e-5f * (0.5f * (1.f - tanhf((v - -83.0f) * FIB_RCPF(23.0)))); });
     const T b_us = map_lanes(V, [](float v) {
@@ -287,7 +287,7 @@ struct Courtemanche {
   static constexpr int MIN_BLOCKS =
       MODE == COURT_FAST ? FIB_COURT_MINB_FAST : (LUT ? FIB_COURT_MINB_LUT : FIB_COURT_MINB_ALL);
   // the one-cell-per-thread flavour of the direct all-state kernel (small grids) keeps 8 CTAs per SM
-  static __host__ __device__ constexpr int min_blocks(int vec) {
+  static __host__ __device__ constexpr int min_blocks(int vec, bool /*phase*/) {
     return (MODE == COURT_ALL && !LUT && vec == 1) ? 8 : MIN_BLOCKS;
   }
   static constexpr bool PACKED = !FIB_ACCURATE_MATH &&
@@ -468,10 +468,10 @@ struct Courtemanche {
     }
     const T Fn = vfma(T((float)(1.0e-15 * V_rel)), i_rel,
                       -(vfma(T(0.5f), i_Ca_L, -(i_NaCa * 0.2f)) * (float)(1.0e-15 / (2.0 * F)))) * 1000.0f;
-    const T u_inf = m_rcp(1.0f + m_exp((Fn - 3.4175e-13f) * -FIB_RCPF(1.367e-15)));
+    const T u_inf = m_rcp(m_exp_affine((Fn - 3.4175e-13f) * -FIB_RCPF(1.367e-15), 1.f, 1.0f));
     s[S_u] = rush_larsen_eb(u, u_inf, T(p.e_u), p.clip_lo, p.clip_hi);
     const T tau_v = vfma(T(2.09f), u_inf, T(1.91f));
-    const T v_inf = 1.0f - m_rcp(1.0f + m_exp((Fn - 6.835e-14f) * -FIB_RCPF(1.367e-15)));
+    const T v_inf = 1.0f - m_rcp(m_exp_affine((Fn - 6.835e-14f) * -FIB_RCPF(1.367e-15), 1.f, 1.0f));
     s[S_v] = rush_larsen_b(v, v_inf, tau_v, nds, p.clip_lo, p.clip_hi);
     const T i_up = m_rcp(1.0f + m_div((float)K_up, Ca_i)) * (float)I_up_max;
     const T i_up_leak = (Ca_up * (float)I_up_max) * FIB_RCPF(Ca_up_max);

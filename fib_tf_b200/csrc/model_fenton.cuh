@@ -6,6 +6,9 @@
 #ifndef FIB_4V_MINB
 #define FIB_4V_MINB 8
 #endif
+#ifndef FIB_4V_MINB_PHASE
+#define FIB_4V_MINB_PHASE 6
+#endif
 #ifndef FIB_4V_PACKED           /* the four cells of a thread as two f2 pairs (packed fp32) */
 #define FIB_4V_PACKED 1
 #endif
@@ -20,7 +23,11 @@ struct Fenton4v {
   static constexpr int MAX_R = 4;
   static constexpr int AUTO_R = 4;   // marching depth picked by launch_step (measured best)
   static constexpr int MIN_BLOCKS = FIB_4V_MINB;
-  static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/) { return MIN_BLOCKS; }
+  // the phase-field flavour holds the phi window as well: at 8 CTAs per SM (64 registers) it spilled 33
+  // values per thread (round-1 ncu); 6 CTAs (80 registers) keeps everything in registers
+  static __host__ __device__ constexpr int min_blocks(int /*cells per thread*/, bool phase) {
+    return phase ? FIB_4V_MINB_PHASE : MIN_BLOCKS;
+  }
   static constexpr bool PACKED = FIB_4V_PACKED != 0;   // the four cells of a thread as two f2 pairs
   static constexpr bool PREFETCH = true;
   static constexpr bool NEED_RAW = true;  // reaction sees the raw U (fenton.py:101), SURVEY fact 3
