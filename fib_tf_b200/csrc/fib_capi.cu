@@ -1027,7 +1027,9 @@ static cudaError_t launch_persist_t(fib_ctx* c, const PersistArgs<MS, MF>& a) {
   attr[0].id = cudaLaunchAttributeCooperative;       // all tiles co-resident, or the launch fails
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // FIB_PERSIST_COOP=0 (experiments only): a plain launch; co-residency then rests on tiles <= SMs alone
+  static const bool coop = !(getenv("FIB_PERSIST_COOP") && atoi(getenv("FIB_PERSIST_COOP")) == 0);
+  cfg.numAttrs = coop ? 1 : 0;
   snprintf(last_kernel_name(), 160, "persist_kernel<%s,TH=%d,PHASE=%d>", MS::name(), TH, PHASE ? 1 : 0);
   return cudaLaunchKernelEx(&cfg, kern, maps, c->g, a);
 }

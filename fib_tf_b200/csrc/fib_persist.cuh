@@ -299,7 +299,6 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         }
       }
     };
-    if (step > 0 && active) ring_poll();
 
     // the three enforced values around my column in local row li
     float T[TH + 2][3];
@@ -323,22 +322,24 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     };
     // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
     // model's cell function; u[]: the raw centre values, T[.][1]: the enforced ones
-    auto do_row = [&](int i) __attribute__((always_inline)) {
+    auto do_row = [&](int i, bool poll_after_lap) __attribute__((always_inline)) {
       float sl[NS], xnew;
 #pragma unroll
       for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
       const float lap = lap_row(i);
+      if (poll_after_lap) ring_poll();
       if (slow) MS::cell(sa_s, u[i], T[i + 1][1], lap, sl, xnew);
       else MF::cell(sa_f, u[i], T[i + 1][1], lap, sl, xnew);
 #pragma unroll
       for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
       u[i] = xnew;
     };
-    auto do_pair = [&](int i, int j) __attribute__((always_inline)) {      // j >= nrows: junk lane, never stored
+    auto do_pair = [&](int i, int j, bool poll_after_lap) __attribute__((always_inline)) {   // j >= nrows: junk lane
       f2 sl[NS], xnew;
 #pragma unroll
       for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
       const f2 lap(lap_row(i), lap_row(j));
+      if (poll_after_lap) ring_poll();
       if (slow) MS::cell(sa_s, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
       else MF::cell(sa_f, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
 #pragma unroll
@@ -348,19 +349,31 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     };
     constexpr bool kPairs = MS::PACKED && MF::PACKED;
 
-    // interior rows: need nothing from outside the tile
+    // interior rows: need nothing from outside the tile.  The FIRST poll of the mailbox goes out in the
+    // middle of this phase: late enough for the neighbours' words (stored at the end of their previous
+    // step, i.e. about when this step began) to have reached L2, early enough for the round trip to be
+    // hidden behind the cell arithmetic.
+    const bool poll = step > 0;
+    bool polled = false;
     if (active) {
 #pragma unroll
       for (int li = 1; li <= TH; ++li) load_row(li);
       if constexpr (kPairs) {
 #pragma unroll
         for (int i = 1; i + 1 < TH - 1; i += 2)
-          if (i < nrows) do_pair(i, i + 1);
+          if (i < nrows) {
+            do_pair(i, i + 1, poll && !polled && i + 3 >= TH - 1);      // before the LAST interior pair's cells
+            polled |= i + 3 >= TH - 1;
+          }
       } else {
 #pragma unroll
         for (int i = 1; i < TH - 1; ++i)
-          if (i < nrows) do_row(i);
+          if (i < nrows) {
+            do_row(i, poll && !polled && i + 2 >= TH - 1);
+            polled |= i + 2 >= TH - 1;
+          }
       }
+      if (poll && !polled) ring_poll();           // (no interior rows: TH = 2, or a short last tile)
     }
     // the neighbours' rows of this step: wait for the mailbox (bounded: raises *err instead of hanging),
     // put them where my stencil reads them
@@ -386,10 +399,10 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
         for (int li = 1; li <= TH; ++li) load_row(li);
       }
       if constexpr (kPairs) {
-        do_pair(0, TH - 1);
+        do_pair(0, TH - 1, false);
       } else {
-        do_row(0);
-        if (TH - 1 < nrows) do_row(TH - 1);
+        do_row(0, false);
+        if (TH - 1 < nrows) do_row(TH - 1, false);
       }
       // (the last step's rows are not consumed through the mailbox: the next launch starts from the plane)
       if (need_top) ll_store(box(want + 1, tile, 0) + c, u[0], want + 1);
