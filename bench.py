@@ -290,7 +290,7 @@ def workload_config(size, n):
 # ---------------------------------------------------------------------------------------------
 # the other kernels / BASELINE configurations, device-timed (N = 1 only): `suite` in the JSON line
 # ---------------------------------------------------------------------------------------------
-def run_suite(device, peak, budget_s=40.0):
+def run_suite(device, peak, budget_s=45.0):
     """Device-timed throughput (CUDA events on the library stream, 3 warm-up iterations) of the 4096^2
     roofline points of every kernel family and of BASELINE configs 1-4 at their own sizes, through the
     drop-in model classes.  frac = B_alg x Gcell-steps/s / measured HBM peak, B_alg = 8 bytes x state
@@ -302,8 +302,12 @@ def run_suite(device, peak, budget_s=40.0):
     from fib_tf_b200.fenton import Fenton4v
     cases = [
         # name, class, N, extra config, hole, B_alg, iterations, slow_every
-        ('config1: 4v 512^2 + hole(256,256,30)', Fenton4v, 512, {'diff': 1.5}, (256, 256, 30), 36, 300, 0),
-        ('config2: BR 512^2 cheby + hole(150,200,40)', BeelerReuter, 512, {'diff': 0.809, 'cheby': True}, (150, 200, 40), 68, 300, 0),
+        ('config1: 4v 512^2 + hole(256,256,30), one fib_step per iteration (driver loop)', Fenton4v, 512, {'diff': 1.5}, (256, 256, 30), 36, 300, 0),
+        ('config1: 4v 512^2 + hole(256,256,30), one fib_step for 300 iterations', Fenton4v, 512, {'diff': 1.5}, (256, 256, 30), 36, 300, -1),
+        ('config1 without the persistent kernel (one launch per step, CUDA graph)', Fenton4v, 512, {'diff': 1.5, 'persist': False}, (256, 256, 30), 36, 300, 0),
+        ('config2: BR 512^2 cheby + hole(150,200,40), one fib_step per iteration (driver loop)', BeelerReuter, 512, {'diff': 0.809, 'cheby': True}, (150, 200, 40), 68, 300, 0),
+        ('config2: BR 512^2 cheby + hole(150,200,40), one fib_step for 300 iterations', BeelerReuter, 512, {'diff': 0.809, 'cheby': True}, (150, 200, 40), 68, 300, -1),
+        ('config2 without the persistent kernel (one launch per step, CUDA graph)', BeelerReuter, 512, {'diff': 0.809, 'cheby': True, 'persist': False}, (150, 200, 40), 68, 300, 0),
         ('config3: BR 2048^2 cheby+skip', BeelerReuter, 2048, {'diff': 0.809, 'cheby': True, 'skip': True}, None, 64, 30, 0),
         ('config4: Courtemanche 2048^2 multi-rate loop (slow every 10)', Courtemanche, 2048, {'diff': 0.809}, None, 168, 60, 10),
         ('config4: Courtemanche 2048^2 ultra + LUT', CourtUltra, 2048, {'diff': 1.5, 'lut': True}, None, 168, 30, 0),
@@ -331,9 +335,12 @@ def run_suite(device, peak, budget_s=40.0):
         c = m._ctx
 
         def go(n):
+            if slow_every < 0:                  # one C-ABI call for all iterations
+                c.step(0, n)
+                return
             for i in range(n):
                 c.step(0, 1)
-                if slow_every and i % slow_every == 0:
+                if slow_every > 0 and i % slow_every == 0:
                     c.step(1, 1)
         go(3)
         c.sync()

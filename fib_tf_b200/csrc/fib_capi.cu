@@ -1035,11 +1035,12 @@ static cudaError_t launch_persist_t(fib_ctx* c, const PersistArgs<MS, MF>& a) {
 }
 
 template <class MS, class MF>
-static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_th) {
+static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_th, int iters) {
   a.x[0] = c->x[0];
   a.x[1] = c->x[1];
   a.cur = c->cur;
-  a.nsteps = substeps_of(c, FIB_OP_ODE);
+  a.period = substeps_of(c, FIB_OP_ODE);
+  a.nsteps = a.period * iters;
   a.mail = c->pmail;
   a.base = c->pbase;
   a.err = c->perr;
@@ -1105,17 +1106,17 @@ static void decide_persist(fib_ctx* c) {
   c->persist = 1;
 }
 
-// one ODE iteration (dt_per_step time steps) as ONE launch
-static int run_iteration_persist(fib_ctx* c) {
+// `iters` ODE iterations (dt_per_step time steps each) as ONE launch
+static int run_iteration_persist(fib_ctx* c, int iters) {
   const double dt = c->cfg.dt;
   const uint32_t fl = c->cfg.flags;
   cudaError_t e;
   if (c->cfg.model == FIB_FENTON4V) {
     PersistArgs<Fenton4v, Fenton4v> a;
-    a.slow_mask = ~0u;
+    a.slow_first_only = 0;
     a.ps.dt = a.pf.dt = (float)dt;
     a.ps.ddt = a.pf.ddt = (float)(c->cfg.diff * dt);
-    e = launch_persist_m<Fenton4v, Fenton4v>(c, a, 8);
+    e = launch_persist_m<Fenton4v, Fenton4v>(c, a, 8, iters);
   } else {
     const bool cheby = fl & FIB_F_CHEBY, strict = cheby && (fl & FIB_F_CHEBY_STRICT), skip = fl & FIB_F_SKIP;
     if (cheby && !c->have_cheb) return fail(FIB_E_STATE, "cheby=True but FIB_TABLE_BR_CHEBY has not been set");
@@ -1123,7 +1124,7 @@ static int run_iteration_persist(fib_ctx* c) {
       using MS = decltype(ts);
       using MF = decltype(tf);
       PersistArgs<MS, MF> a;
-      a.slow_mask = skip ? 1u : ~0u;                                                  // br.py:96-107
+      a.slow_first_only = skip ? 1 : 0;                                               // br.py:96-107
       auto fill = [&](auto& p, int n) {
         p.dt = (float)dt;
         p.neg_dt = (float)(-dt);
@@ -1135,7 +1136,7 @@ static int run_iteration_persist(fib_ctx* c) {
       };
       fill(a.ps, skip ? 5 : 1);
       fill(a.pf, 0);
-      return launch_persist_m<MS, MF>(c, a, 4);
+      return launch_persist_m<MS, MF>(c, a, 4, iters);
     };
     if (strict)     e = go(BeelerReuter<2, true>(), BeelerReuter<2, false>());
     else if (cheby) e = go(BeelerReuter<1, true>(), BeelerReuter<1, false>());
@@ -1149,15 +1150,16 @@ static int run_iteration_persist(fib_ctx* c) {
     return 1;           // caller retries on the plain path
   }
   c->launches++;
-  const int ns = substeps_of(c, FIB_OP_ODE);
+  const int ns = substeps_of(c, FIB_OP_ODE) * iters;
   c->pbase += (unsigned)ns;
   if (ns & 1) c->cur ^= 1;
   if (c->ptimeline) {          // diagnostics: print the middle tile's phase times of this launch
     cudaStreamSynchronize(c->stream);
     const unsigned long long* tl = c->ptimeline;
     fprintf(stderr, "persist timeline (ns): load %llu |", tl[1] - tl[0]);
-    for (int k = 0; k < ns; ++k) fprintf(stderr, " %llu", tl[2 + k] - tl[1 + k]);
-    fprintf(stderr, " | store %llu | total %llu\n", tl[2 + ns] - tl[1 + ns], tl[2 + ns] - tl[0]);
+    for (int k = 0; k < ns && k < 12; ++k) fprintf(stderr, " %llu", tl[2 + k] - tl[1 + k]);
+    if (ns <= 12) fprintf(stderr, " | store %llu | total %llu", tl[2 + ns] - tl[1 + ns], tl[2 + ns] - tl[0]);
+    fprintf(stderr, "\n");
   }
   return 0;
 }
@@ -1254,12 +1256,17 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
     return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
   if (c->persist < 0) decide_persist(c);
   if (c->persist == 1 && op == FIB_OP_ODE) {
+    // fib_step(n_iter > 1) with no probe being watched: up to kPersistMaxIters iterations per launch
+    // (no launch gap, no tile reload between them); with a watch every iteration is its own launch
+    // because the probe is recorded between iterations
     int i = 0;
-    for (; i < n_iter; ++i) {
-      int r = run_iteration_persist(c);
+    while (i < n_iter) {
+      const int batch = (c->watch_var >= 0 || c->ptimeline) ? 1 : min(n_iter - i, kPersistMaxIters);
+      int r = run_iteration_persist(c, batch);
       if (r > 0) break;                 // could not launch: plain path from here on
       if (r) return r;
       if ((r = record_probe(c, op))) return r;
+      i += batch;
     }
     if (i == n_iter) return 0;
     n_iter -= i;

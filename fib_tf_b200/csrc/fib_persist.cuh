@@ -93,7 +93,7 @@ __device__ __forceinline__ void ll_load(const unsigned long long* p, float& v, u
   step = b;
 }
 // ---- arguments --------------------------------------------------------------------------------
-constexpr int kPersistMaxSteps = 10;
+constexpr int kPersistMaxIters = 64;      // run() iterations one launch may cover (fib_step with n_iter > 1)
 
 template <int NS>
 struct PersistMaps {
@@ -106,7 +106,8 @@ struct PersistArgs {
   float* x[2];                 // the same two buffers as plain pointers (halo layout: row g at (g + 1) * pitch)
   int cur;                     // x[cur] holds the state at the start of the launch
   int nsteps;                  // time steps of this launch (dt_per_step)
-  unsigned slow_mask;          // bit s: step s is an MS step (e.g. BR n > 0), else MF (BR n == 0)
+  int period;                  // time steps per run() iteration (dt_per_step); a launch may cover several iterations
+  int slow_first_only;         // 1: only the first step of every iteration is an MS step (br.py's skip schedule), 0: all
   unsigned long long* mail;    // the mailbox (persist_mailbox_words), words {value, step number}
   unsigned base;               // step number of the state at the start of this launch (monotonic over the run)
   int* err;                    // set to 1 if a neighbour wait ran into the spin limit
@@ -278,7 +279,7 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
 
   for (int step = 0; step < a.nsteps; ++step) {
     const int p = step & 1;                                  // shared buffer holding the state this step reads
-    const bool slow = (a.slow_mask >> step) & 1u;
+    const bool slow = !a.slow_first_only || step % a.period == 0;
     const unsigned want = a.base + step;                     // step number of that state
     // My six mailbox words (three columns on each side).  All six loads are issued back to back, so one
     // poll costs ONE L2 round trip; the first poll is issued BEFORE the interior rows are advanced and only

@@ -15,13 +15,19 @@ m = (Fenton4v if kind == '4v' else BeelerReuter)(cfg)
 m.add_hole_to_phase_field(*((256, 256, 30) if kind == '4v' else (150, 200, 40)))
 m.define()
 c = m._ctx
-c.step(0, 3)
-c.sync()
-c.timer_start()
-c.step(0, iters)
-c.timer_stop()
-ms = c.timer_ms()
 steps = iters * m.dt_per_step
-print('%s 512^2: %.2f us per time step, %.1f Gcell-steps/s (%d launches)' % (
-    kind, ms * 1e3 / steps, 512 * 512 * steps / ms / 1e6, c.launch_count()))
+for mode in ('one fib_step call per iteration (the driver loop)', 'one fib_step call for all iterations'):
+    c.step(0, 3)
+    c.sync()
+    n0 = c.launch_count()
+    c.timer_start()
+    if mode.startswith('one fib_step call per'):
+        for _ in range(iters):
+            c.step(0, 1)
+    else:
+        c.step(0, iters)
+    c.timer_stop()
+    ms = c.timer_ms()
+    print('%s 512^2, %s: %.2f us per time step, %.1f Gcell-steps/s (%d launches)' % (
+        kind, mode, ms * 1e3 / steps, 512 * 512 * steps / ms / 1e6, c.launch_count() - n0))
 m.close()

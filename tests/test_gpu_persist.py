@@ -69,8 +69,8 @@ def test_fenton_persistent_kernel_is_bit_identical(cuda, H, W, th, hole):
         want = ref.get_state(v)
         assert np.isfinite(want).all()
         assert np.array_equal(per.get_state(v), want), v
-    # ONE launch per iteration (+ the stimulus kernel)
-    assert per.launch_count() - n_per == 7 + 1 and ref.launch_count() - n_ref == 70 + 1
+    # ONE launch per fib_step call: four single iterations + three iterations in one launch (+ the stimulus)
+    assert per.launch_count() - n_per == 4 + 1 + 1 and ref.launch_count() - n_ref == 70 + 1
     per.close()
     ref.close()
 
