@@ -386,6 +386,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner off it
+        os.environ['NCCL_DEBUG'] = os.environ.get('FIB_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     K, Wm, size = args.steps, max(args.warmup, 3), args.size
 
