@@ -87,6 +87,7 @@ _SIGNATURES = {
     'fib_set_weights': (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int]),
     'fib_masked_sum': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'fib_sync': (C.c_int, [_P]),
+    'fib_flush': (C.c_int, [_P]),
     'fib_timer_start': (C.c_int, [_P]),
     'fib_timer_stop': (C.c_int, [_P]),
     'fib_timer_ms': (C.c_int, [_P, _FP]),
@@ -312,6 +313,10 @@ class Context:
 
     def sync(self):
         check(lib().fib_sync(self._h))
+
+    def flush(self):
+        """Launch the iterations the persistent path has deferred (enqueue only)."""
+        check(lib().fib_flush(self._h))
 
     def timer_start(self):
         check(lib().fib_timer_start(self._h))

@@ -132,9 +132,16 @@ struct fib_ctx {
   std::vector<GraphKey> graphs;
   double* red = nullptr;              // 2 doubles for reductions
   // device-side cycle-length probe (fib_probe_watch): one watched cell, a ring of recorded values
-  float* ring = nullptr;
-  unsigned long long* ring_count = nullptr;
+  float* ring = nullptr;              // page-locked, device-visible: a fetch is a stream sync + host reads
+  unsigned long long* ring_count = nullptr;   // device: the slot the next record goes to
+  unsigned long long ring_total = 0;  // host mirror of *ring_count once the stream has drained
   unsigned long long ring_fetched = 0;
+  // the last few persistent launches that recorded probes: {event after the launch, ring_total after it};
+  // a fetch of older values waits for the covering event only, not for the launches queued behind it
+  static constexpr int kRingEvents = 4;
+  cudaEvent_t ring_ev[kRingEvents] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long ring_ev_total[kRingEvents] = {0, 0, 0, 0};
+  int ring_ev_next = 0;
   int watch_var = -1, watch_row = -1, watch_col = -1;
   float* weights[4] = {nullptr, nullptr, nullptr, nullptr};   // user masks, halo layout like phase
   // persistent on-chip kernel (fib_persist.cuh): small unsharded 4v / BR grids
@@ -142,6 +149,7 @@ struct fib_ctx {
   int persist_th = 0, persist_tiles = 0, persist_bw = 0;
   unsigned long long* pmail = nullptr;   // edge-row mailbox of the persistent kernel, words {value, step number}
   unsigned pbase = 0;
+  int pending = 0;                    // ODE iterations accepted by fib_step but not launched yet (see flush_pending)
   int* perr = nullptr;                // page-locked, device-visible: raised by a timed-out neighbour wait
   unsigned long long* ptimeline = nullptr;   // page-locked [16], FIB_PERSIST_TIMELINE=1 only
   CUtensorMap pmap_x[2], pmap_s[8];
@@ -500,7 +508,9 @@ extern "C" int fib_destroy(fib_ctx* c) {
   cudaFree(c->lut);
   cudaFree(c->lut_t);
   cudaFree(c->red);
-  cudaFree(c->ring);
+  cudaFreeHost(c->ring);
+  for (auto& e : c->ring_ev)
+    if (e) cudaEventDestroy(e);
   cudaFree(c->ring_count);
   cudaFree(c->pmail);
   if (c->perr) cudaFreeHost(c->perr);
@@ -551,6 +561,7 @@ static void mark_written(fib_ctx* c, int var) {
     const float* src = p.base + (size_t)(p.halo + c->watch_row - c->g.row0) * c->g.pitch + c->watch_col;
     probe_update_kernel<<<1, 1, 0, c->stream>>>(src, c->ring, c->ring_count);
     c->launches++;
+    for (auto& t : c->ring_ev_total) t = 0;     // a recorded value changes after its launch's event
   }
 }
 // a halo exchange still running on the side stream must land before anything else touches the
@@ -561,12 +572,26 @@ static cudaError_t wait_comm(fib_ctx* c) {
   return cudaStreamWaitEvent(c->stream, c->ev_comm, 0);
 }
 
+// The persistent path DEFERS iterations: fib_step only counts them, and they are launched -- up to
+// kPersistMaxIters per launch -- by the next call that observes or modifies anything (every entry
+// point below starts with FLUSH), or as soon as a full launch's worth has accumulated.  A driver
+// loop of fib_step(ctx, op, 1) calls then costs one launch per 64 iterations instead of one each.
+static int flush_pending(fib_ctx* c);
+#define FLUSH(c)                                                      \
+  do {                                                                \
+    if ((c)->pending) {                                               \
+      const int fr_ = flush_pending(c);                               \
+      if (fr_) return fr_;                                            \
+    }                                                                 \
+  } while (0)
+
 extern "C" int fib_set_state(fib_ctx* c, int var, const float* host, size_t n) {
   if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   if (n != (size_t)c->g.rows * c->g.W)
     return fail(FIB_E_ARG, "fib_set_state: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(wait_comm(c));
   CU(cudaMemcpy2DAsync(owned_rows(c, var), c->g.pitch * sizeof(float), host, c->g.W * sizeof(float),
                        c->g.W * sizeof(float), c->g.rows, cudaMemcpyHostToDevice, c->stream));
@@ -581,6 +606,7 @@ extern "C" int fib_get_state(fib_ctx* c, int var, float* host, size_t n) {
   if (n != (size_t)c->g.rows * c->g.W)
     return fail(FIB_E_ARG, "fib_get_state: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaMemcpy2DAsync(host, c->g.W * sizeof(float), owned_rows(c, var), c->g.pitch * sizeof(float),
                        c->g.W * sizeof(float), c->g.rows, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -593,6 +619,7 @@ extern "C" int fib_get_rect(fib_ctx* c, int var, int r0, int r1, int c0, int c1,
   if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
     return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   const float* src = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch + c0;
   CU(cudaMemcpy2DAsync(host, (size_t)(c1 - c0) * sizeof(float), src, c->g.pitch * sizeof(float),
                        (size_t)(c1 - c0) * sizeof(float), r1 - r0, cudaMemcpyDeviceToHost, c->stream));
@@ -606,6 +633,7 @@ extern "C" int fib_snapshot_begin(fib_ctx* c, int var, float* host_pinned, size_
   if (n != (size_t)c->g.rows * c->g.W)
     return fail(FIB_E_ARG, "fib_snapshot_begin: n=%zu, expected rows*width=%zu", n, (size_t)c->g.rows * c->g.W);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, host_pinned) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
@@ -630,6 +658,7 @@ extern "C" int fib_snapshot_wait(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   if (!c->snap_pending) return 0;
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaEventSynchronize(c->ev_snap_done));
   c->snap_pending = false;
   return 0;
@@ -641,6 +670,7 @@ static int set_rect_impl(fib_ctx* c, int var, int r0, int r1, int c0, int c1, co
   if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
     return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   if (!sync) {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
@@ -666,6 +696,7 @@ extern "C" int fib_set_rect_async(fib_ctx* c, int var, int r0, int r1, int c0, i
 extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, int nrows) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaStreamSynchronize(c->stream));
   for (auto& gk : c->graphs) cudaGraphExecDestroy(gk.exec);   // graphs bake the phase pointer in
   c->graphs.clear();
@@ -731,6 +762,7 @@ extern "C" int fib_set_phase(fib_ctx* c, const float* rows_host, int first_row, 
 extern "C" int fib_set_table(fib_ctx* c, int table, const float* data, size_t n) {
   if (!c || !data) return fail(FIB_E_ARG, "ctx/data is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   if (table == FIB_TABLE_BR_CHEBY) {
     if (n != 12 * 9) return fail(FIB_E_ARG, "BR Chebyshev table must hold 12*9 floats, got %zu", n);
     CU(cudaStreamSynchronize(c->stream));
@@ -758,6 +790,7 @@ extern "C" int fib_set_table(fib_ctx* c, int table, const float* data, size_t n)
 extern "C" int fib_get_table(fib_ctx* c, int table, float* data, size_t n) {
   if (!c || !data) return fail(FIB_E_ARG, "ctx/data is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   if (table == FIB_TABLE_BR_CHEBY) {
     if (n != 12 * 9) return fail(FIB_E_ARG, "BR Chebyshev table holds 12*9 floats");
     memcpy(data, c->cheb, sizeof c->cheb);
@@ -777,6 +810,7 @@ extern "C" int fib_build_lut(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   if (!c->lut) return fail(FIB_E_STATE, "this model has no lookup table");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   court_lut_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut);
   CU(cudaGetLastError());
   lut_transpose_kernel<<<(kLutRows + 63) / 64, 64, 0, c->stream>>>(c->lut, c->lut_t);
@@ -790,6 +824,7 @@ extern "C" int fib_court_inter(fib_ctx* c, const float* v_host, size_t n, float*
   if (!c || !v_host || !out_host) return fail(FIB_E_ARG, "NULL argument");
   if (n == 0) return 0;
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   struct Tmp {
     float* p = nullptr;
     ~Tmp() { cudaFree(p); }
@@ -1049,6 +1084,11 @@ static cudaError_t launch_persist_m(fib_ctx* c, PersistArgs<MS, MF>& a, int max_
   a.pmask = c->pmask;
   a.pmask_pitch = c->pmask_pitch;
   a.bw = c->persist_bw;
+  a.ring = c->watch_var >= 0 ? c->ring : nullptr;
+  a.ring_count = c->ring_count;
+  a.probe_var = c->watch_var;
+  a.probe_row = c->watch_row;
+  a.probe_col = c->watch_col;
   const bool ph = c->phase != nullptr;
   (void)max_th;
   switch (c->persist_th) {
@@ -1150,6 +1190,14 @@ static int run_iteration_persist(fib_ctx* c, int iters) {
     return 1;           // caller retries on the plain path
   }
   c->launches++;
+  if (c->watch_var >= 0) {
+    c->ring_total += (unsigned)iters;
+    const int k = c->ring_ev_next;
+    if (c->ring_ev[k] && cudaEventRecord(c->ring_ev[k], c->stream) == cudaSuccess) {
+      c->ring_ev_total[k] = c->ring_total;
+      c->ring_ev_next = (k + 1) % fib_ctx::kRingEvents;
+    }
+  }
   const int ns = substeps_of(c, FIB_OP_ODE) * iters;
   c->pbase += (unsigned)ns;
   if (ns & 1) c->cur ^= 1;
@@ -1180,6 +1228,7 @@ static int record_probe(fib_ctx* c, int op) {
   probe_record_kernel<<<1, 1, 0, c->stream>>>(src, c->ring, c->ring_count);
   CU(cudaGetLastError());
   c->launches++;
+  c->ring_total++;
   return 0;
 }
 
@@ -1239,12 +1288,8 @@ static int refresh_halos_nccl(fib_ctx* c) {
   return 0;
 }
 
-extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
-  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
-  if (op != FIB_OP_ODE && op != FIB_OP_SLOW) return fail(FIB_E_ARG, "unknown op %d", op);
-  if (n_iter < 0) return fail(FIB_E_ARG, "n_iter < 0");
-  if (substeps_of(c, op) == 0 || n_iter == 0) return 0;
-  DevGuard dg(c->cfg.device);
+// n_iter iterations of `op`, enqueued now
+static int step_now(fib_ctx* c, int op, int n_iter) {
   if (c->comm) {
     int r = refresh_halos_nccl(c);
     if (r) return r;
@@ -1252,20 +1297,15 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
       if ((r = run_iteration_nccl(c, op))) return r;
     return 0;
   }
-  if (c->g.rows != c->g.H)
-    return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
-  if (c->persist < 0) decide_persist(c);
   if (c->persist == 1 && op == FIB_OP_ODE) {
-    // fib_step(n_iter > 1) with no probe being watched: up to kPersistMaxIters iterations per launch
-    // (no launch gap, no tile reload between them); with a watch every iteration is its own launch
-    // because the probe is recorded between iterations
+    // up to kPersistMaxIters iterations per launch (no launch gap, no tile reload between them); a
+    // watched probe is recorded by the kernel itself after every iteration
     int i = 0;
     while (i < n_iter) {
-      const int batch = (c->watch_var >= 0 || c->ptimeline) ? 1 : min(n_iter - i, kPersistMaxIters);
+      const int batch = c->ptimeline ? 1 : min(n_iter - i, kPersistMaxIters);
       int r = run_iteration_persist(c, batch);
       if (r > 0) break;                 // could not launch: plain path from here on
       if (r) return r;
-      if ((r = record_probe(c, op))) return r;
       i += batch;
     }
     if (i == n_iter) return 0;
@@ -1288,11 +1328,13 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
       cudaGraph_t graph = nullptr;
       CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       const uint64_t l0 = c->launches;
+      const unsigned long long rt0 = c->ring_total;
       pdl_enabled() = false;               // plain kernel nodes replay faster (see fib_kernels.cuh)
       int r = run_iteration_plain(c, op);
       pdl_enabled() = true;
       cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
       c->launches = l0;
+      c->ring_total = rt0;
       c->cur = cur0;
       if (r) { if (graph) cudaGraphDestroy(graph); return r; }
       if (ce != cudaSuccess) return fail(FIB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1302,10 +1344,43 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
     }
     CU(cudaGraphLaunch(exec, c->stream));
     const int nl = substeps_of(c, op) / c->fuse;      // step launches per iteration
-    c->launches += nl + ((c->watch_var >= 0 && op == FIB_OP_ODE) ? 1 : 0);
+    const int rec = (c->watch_var >= 0 && op == FIB_OP_ODE) ? 1 : 0;
+    c->launches += nl + rec;
+    c->ring_total += rec;
     if (op_writes_x(c, op) && (nl & 1)) c->cur ^= 1;
   }
   return 0;
+}
+
+static int flush_pending(fib_ctx* c) {
+  const int n = c->pending;
+  c->pending = 0;
+  return n ? step_now(c, FIB_OP_ODE, n) : 0;
+}
+
+extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (op != FIB_OP_ODE && op != FIB_OP_SLOW) return fail(FIB_E_ARG, "unknown op %d", op);
+  if (n_iter < 0) return fail(FIB_E_ARG, "n_iter < 0");
+  if (substeps_of(c, op) == 0 || n_iter == 0) return 0;
+  DevGuard dg(c->cfg.device);
+  if (!c->comm && c->g.rows != c->g.H)
+    return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
+  if (!c->comm && c->persist < 0) decide_persist(c);
+  if (c->persist == 1 && op == FIB_OP_ODE && !c->ptimeline) {
+    // persistent path: count now, launch later (see FLUSH); whatever can fail is checked here
+    if (c->cfg.model == FIB_BR && (c->cfg.flags & FIB_F_CHEBY) && !c->have_cheb)
+      return fail(FIB_E_STATE, "cheby=True but FIB_TABLE_BR_CHEBY has not been set");
+    while (n_iter > 0) {
+      const int take = min(n_iter, kPersistMaxIters - c->pending);
+      c->pending += take;
+      n_iter -= take;
+      if (c->pending == kPersistMaxIters) FLUSH(c);
+    }
+    return 0;
+  }
+  FLUSH(c);
+  return step_now(c, op, n_iter);
 }
 
 // ---- in-process shard group: lock-step, device-to-device halo copies ------------------------
@@ -1366,6 +1441,10 @@ extern "C" int fib_step_group(fib_ctx** cs, int n, int op, int n_iter) {
     row += cs[i]->g.rows;
   }
   if (row != cs[0]->g.H) return fail(FIB_E_ARG, "shards cover %d of %d rows", row, cs[0]->g.H);
+  for (int i = 0; i < n; ++i) {
+    DevGuard dg(cs[i]->cfg.device);
+    FLUSH(cs[i]);
+  }
   // shards on different devices of this process: direct NVLink copies need peer access
   for (int i = 0; i + 1 < n; ++i) {
     const int a = cs[i]->cfg.device, b = cs[i + 1]->cfg.device;
@@ -1418,6 +1497,7 @@ extern "C" int fib_stimulate(fib_ctx* c, int var, int r0, int r1, int c0, int c1
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(wait_comm(c));
   dim3 block(128), grid((c->g.W + 127) / 128, min(c->g.rows, 65535));
   const PlaneRef pl = plane_of(c, var);
@@ -1434,6 +1514,7 @@ extern "C" int fib_probe(fib_ctx* c, int var, int row, int col, float* out) {
   if (row < c->g.row0 || row >= c->g.row0 + c->g.rows || col < 0 || col >= c->g.W)
     return fail(FIB_E_ARG, "probe (%d,%d) is not in this shard", row, col);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaMemcpyAsync(out, owned_rows(c, var) + (size_t)(row - c->g.row0) * c->g.pitch + col,
                      sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1445,6 +1526,7 @@ extern "C" int fib_weighted_sum(fib_ctx* c, int var, double* sum_wx, double* sum
   if (!c || !sum_wx || !sum_w) return fail(FIB_E_ARG, "NULL argument");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   return reduce_weighted(c, var, c->phase, sum_wx, sum_w);
 }
 
@@ -1466,6 +1548,7 @@ extern "C" int fib_count_nonfinite(fib_ctx* c, int var, uint64_t* count) {
   if (!c || !count) return fail(FIB_E_ARG, "ctx/count is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
   const PlaneRef pl = plane_of(c, var);
   nonfinite_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(
@@ -1485,6 +1568,7 @@ extern "C" int fib_set_weights(fib_ctx* c, int slot, const float* rows_host, int
   if (first_row > c->g.row0 || first_row + nrows < c->g.row0 + c->g.rows)
     return fail(FIB_E_ARG, "weight rows [%d,%d) do not cover this shard", first_row, first_row + nrows);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   if (!c->weights[slot]) {
     CU(cudaMalloc(&c->weights[slot], c->halo_floats() * sizeof(float)));
     CU(cudaMemsetAsync(c->weights[slot], 0, c->halo_floats() * sizeof(float), c->stream));
@@ -1501,6 +1585,7 @@ extern "C" int fib_masked_sum(fib_ctx* c, int var, int slot, double* sum_wx, dou
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   if (slot < 0 || slot >= 4 || !c->weights[slot]) return fail(FIB_E_STATE, "weight slot %d is empty", slot);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   return reduce_weighted(c, var, c->weights[slot], sum_wx, sum_w);
 }
 
@@ -1512,6 +1597,7 @@ static void drop_graphs(fib_ctx* c) {
 extern "C" int fib_probe_watch(fib_ctx* c, int var, int row, int col) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaStreamSynchronize(c->stream));
   drop_graphs(c);                       // the record node is part of the iteration graph
   if (row < 0) {
@@ -1522,11 +1608,16 @@ extern "C" int fib_probe_watch(fib_ctx* c, int var, int row, int col) {
   if (row < c->g.row0 || row >= c->g.row0 + c->g.rows || col < 0 || col >= c->g.W)
     return fail(FIB_E_ARG, "probe (%d,%d) is not in this shard", row, col);
   if (!c->ring) {
-    CU(cudaMalloc(&c->ring, FIB_PROBE_RING * sizeof(float)));
+    CU(cudaHostAlloc(&c->ring, FIB_PROBE_RING * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
     CU(cudaMalloc(&c->ring_count, sizeof(unsigned long long)));
   }
   CU(cudaMemsetAsync(c->ring_count, 0, sizeof(unsigned long long), c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < fib_ctx::kRingEvents; ++k) {
+    if (!c->ring_ev[k]) CU(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
+    c->ring_ev_total[k] = 0;
+  }
+  c->ring_total = 0;
   c->ring_fetched = 0;
   c->watch_var = var;
   c->watch_row = row;
@@ -1539,9 +1630,26 @@ extern "C" int fib_probe_fetch(fib_ctx* c, float* out, size_t max, size_t* n) {
   *n = 0;
   if (c->watch_var < 0) return fail(FIB_E_STATE, "no probe is being watched (fib_probe_watch)");
   DevGuard dg(c->cfg.device);
-  unsigned long long count = 0;
-  CU(cudaMemcpyAsync(&count, c->ring_count, sizeof count, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  FLUSH(c);
+  // The records land in page-locked host memory.  Asked for fewer values than were recorded, wait only
+  // for the launch that produced the last of them (the later ones keep the GPU busy meanwhile).
+  unsigned long long count = c->ring_total;
+  if (count - c->ring_fetched > max) {
+    const unsigned long long need = c->ring_fetched + max;
+    int best = -1;
+    for (int k = 0; k < fib_ctx::kRingEvents; ++k)
+      if (c->ring_ev_total[k] >= need && c->ring_ev_total[k] <= c->ring_total &&
+          (best < 0 || c->ring_ev_total[k] < c->ring_ev_total[best]))
+        best = k;
+    if (best >= 0) {
+      CU(cudaEventSynchronize(c->ring_ev[best]));
+      count = c->ring_ev_total[best];
+    } else {
+      CU(cudaStreamSynchronize(c->stream));
+    }
+  } else {
+    CU(cudaStreamSynchronize(c->stream));
+  }
   unsigned long long first = c->ring_fetched;
   if (count - first > FIB_PROBE_RING) first = count - FIB_PROBE_RING;      // the oldest were overwritten
   unsigned long long take = count - first;
@@ -1552,10 +1660,9 @@ extern "C" int fib_probe_fetch(fib_ctx* c, float* out, size_t max, size_t* n) {
     const unsigned long long pos = (first + done) % FIB_PROBE_RING;
     unsigned long long len = FIB_PROBE_RING - pos;
     if (len > take - done) len = take - done;
-    CU(cudaMemcpyAsync(out + done, c->ring + pos, len * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    memcpy(out + done, c->ring + pos, len * sizeof(float));
     done += len;
   }
-  CU(cudaStreamSynchronize(c->stream));
   c->ring_fetched = first + take;
   *n = (size_t)take;
   return 0;
@@ -1566,6 +1673,7 @@ extern "C" int fib_count_below(fib_ctx* c, int var, float sub, float div, float 
   if (!c || !below || !total) return fail(FIB_E_ARG, "NULL argument");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaMemsetAsync(c->red, 0, 2 * sizeof(double), c->stream));
   const PlaneRef pl = plane_of(c, var);
   count_below_kernel<<<min(c->g.rows, 4 * c->sms), 256, 0, c->stream>>>(
@@ -1660,21 +1768,30 @@ extern "C" int fib_op_rush_larsen(int device, const float* g, const float* g_inf
 extern "C" int fib_sync(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->comm_stream));
   CU(cudaStreamSynchronize(c->copy_stream));
   c->snap_pending = false;
   return check_persist_error(c);
 }
+extern "C" int fib_flush(fib_ctx* c) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  DevGuard dg(c->cfg.device);
+  FLUSH(c);
+  return 0;
+}
 extern "C" int fib_timer_start(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   CU(cudaEventRecord(c->ev_start, c->stream));
   return 0;
 }
 extern "C" int fib_timer_stop(fib_ctx* c) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   if (c->comm_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
   CU(cudaEventRecord(c->ev_stop, c->stream));
   return 0;
@@ -1688,11 +1805,15 @@ extern "C" int fib_timer_ms(fib_ctx* c, float* ms) {
 }
 extern "C" int fib_launch_count(const fib_ctx* c, uint64_t* kernels) {
   if (!c || !kernels) return fail(FIB_E_ARG, "ctx/kernels is NULL");
+  DevGuard dg(c->cfg.device);
+  FLUSH(const_cast<fib_ctx*>(c));       // deferred iterations count once they are launched
   *kernels = c->launches;
   return 0;
 }
 extern "C" int fib_stream(const fib_ctx* c, void** cuda_stream) {
   if (!c || !cuda_stream) return fail(FIB_E_ARG, "ctx/out is NULL");
+  DevGuard dg(c->cfg.device);
+  FLUSH(const_cast<fib_ctx*>(c));
   *cuda_stream = (void*)c->stream;
   return 0;
 }
@@ -1719,6 +1840,7 @@ extern "C" int fib_comm_init(fib_ctx* c, int nranks, int rank, const void* id128
   int r = nccl_load();
   if (r) return r;
   DevGuard dg(c->cfg.device);
+  FLUSH(c);
   Uid uid;
   memcpy(uid.bytes, id128, sizeof uid.bytes);
   NC(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));

@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #ifndef FIB_ACCURATE_MATH
 #define FIB_ACCURATE_MATH 0
 #endif
@@ -234,5 +236,15 @@ template <class T> __device__ __forceinline__ T m_half_1p_tanh(T z) {
   return sfu_rcp(m_exp_affine(T(-2.0f) * z, 1.0f, 1.0f));
 }
 #endif
+
+// The Laplacian enters a cell function only in its last expression.  A cell function takes it either
+// as a value or as a callable evaluated at that point: the persistent kernel passes a callable that
+// first waits for the neighbour tiles' rows, so everything of the cell that does not depend on them
+// is already computed when they arrive (fib_persist.cuh).
+template <class T, class L>
+__device__ __forceinline__ T lap_value(const L& lap) {
+  if constexpr (std::is_convertible<L, T>::value) return lap;
+  else return lap();
+}
 
 }  // namespace fib

@@ -117,6 +117,12 @@ struct PersistArgs {
   const unsigned char* pmask;  // [rows][pmask_pitch] as in StepArgs
   int pmask_pitch;
   int bw;                      // TMA box width actually encoded (min(256, W rounded up to 4))
+  // fib_probe_watch (or ring == nullptr): the thread owning cell (probe_row, probe_col) appends plane
+  // probe_var (0 = the diffusing variable, k = state plane k - 1) to the ring after every iteration,
+  // exactly what probe_record_kernel does between the iterations of the one-launch-per-step path
+  float* ring;
+  unsigned long long* ring_count;
+  int probe_var, probe_row, probe_col;
   typename MS::Params ps;      // parameters of the MS steps
   typename MF::Params pf;      // parameters of the MF steps
 };
@@ -277,9 +283,17 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
     return a.mail + (((size_t)(n & 1u) * ntiles + tl) * 2 + sd) * kPersistThreads;
   };
 
+  // local rows 1..TH show rows of my own tile (everywhere but on a one-row last tile, whose row H-1 shows H-2)
+  bool lazy = true;
+#pragma unroll
+  for (int li = 1; li <= TH; ++li)
+    if (src[li] == 0 || src[li] == TH + 1) lazy = false;
+  const bool probe_me = a.ring && active && c == a.probe_col && a.probe_row >= r0 && a.probe_row < r0 + nrows;
+  unsigned long long probe_n = probe_me ? *a.ring_count : 0ull;
+  int sub = 0;                                               // time step within the current iteration
   for (int step = 0; step < a.nsteps; ++step) {
     const int p = step & 1;                                  // shared buffer holding the state this step reads
-    const bool slow = !a.slow_first_only || step % a.period == 0;
+    const bool slow = !a.slow_first_only || sub == 0;
     const unsigned want = a.base + step;                     // step number of that state
     // My six mailbox words (three columns on each side).  All six loads are issued back to back, so one
     // poll costs ONE L2 round trip; the first poll is issued BEFORE the interior rows are advanced and only
@@ -322,27 +336,24 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       return lap;
     };
     // one cell (row i) / two cells (rows i and j of my column as ONE packed pair, fib_math.cuh) through the
-    // model's cell function; u[]: the raw centre values, T[.][1]: the enforced ones
-    auto do_row = [&](int i, bool poll_after_lap) __attribute__((always_inline)) {
+    // model's cell function; u[]: the raw centre values, T[.][1]: the enforced ones.  `lapf` yields the
+    // Laplacian(s) when the cell function gets to its last expression (lap_value, fib_math.cuh).
+    auto do_row = [&](int i, auto&& lapf) __attribute__((always_inline)) {
       float sl[NS], xnew;
 #pragma unroll
       for (int k = 0; k < NS; ++k) sl[k] = s[k][i];
-      const float lap = lap_row(i);
-      if (poll_after_lap) ring_poll();
-      if (slow) MS::cell(sa_s, u[i], T[i + 1][1], lap, sl, xnew);
-      else MF::cell(sa_f, u[i], T[i + 1][1], lap, sl, xnew);
+      if (slow) MS::cell(sa_s, u[i], T[i + 1][1], lapf, sl, xnew);
+      else MF::cell(sa_f, u[i], T[i + 1][1], lapf, sl, xnew);
 #pragma unroll
       for (int k = 0; k < NS; ++k) s[k][i] = sl[k];
       u[i] = xnew;
     };
-    auto do_pair = [&](int i, int j, bool poll_after_lap) __attribute__((always_inline)) {   // j >= nrows: junk lane
+    auto do_pair = [&](int i, int j, auto&& lapf) __attribute__((always_inline)) {   // j >= nrows: junk lane
       f2 sl[NS], xnew;
 #pragma unroll
       for (int k = 0; k < NS; ++k) sl[k] = f2(s[k][i], s[k][j]);
-      const f2 lap(lap_row(i), lap_row(j));
-      if (poll_after_lap) ring_poll();
-      if (slow) MS::cell(sa_s, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
-      else MF::cell(sa_f, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lap, sl, xnew);
+      if (slow) MS::cell(sa_s, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lapf, sl, xnew);
+      else MF::cell(sa_f, f2(u[i], u[j]), f2(T[i + 1][1], T[j + 1][1]), lapf, sl, xnew);
 #pragma unroll
       for (int k = 0; k < NS; ++k) { s[k][i] = sl[k].x; s[k][j] = sl[k].y; }
       u[i] = xnew.x;
@@ -363,22 +374,26 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
 #pragma unroll
         for (int i = 1; i + 1 < TH - 1; i += 2)
           if (i < nrows) {
-            do_pair(i, i + 1, poll && !polled && i + 3 >= TH - 1);      // before the LAST interior pair's cells
+            const f2 lap(lap_row(i), lap_row(i + 1));
+            if (poll && !polled && i + 3 >= TH - 1) ring_poll();       // before the LAST interior pair's cells
             polled |= i + 3 >= TH - 1;
+            do_pair(i, i + 1, lap);
           }
       } else {
 #pragma unroll
         for (int i = 1; i < TH - 1; ++i)
           if (i < nrows) {
-            do_row(i, poll && !polled && i + 2 >= TH - 1);
+            const float lap = lap_row(i);
+            if (poll && !polled && i + 2 >= TH - 1) ring_poll();
             polled |= i + 2 >= TH - 1;
+            do_row(i, lap);
           }
       }
       if (poll && !polled) ring_poll();           // (no interior rows: TH = 2, or a short last tile)
     }
     // the neighbours' rows of this step: wait for the mailbox (bounded: raises *err instead of hanging),
     // put them where my stencil reads them
-    if (step > 0 && active) {
+    auto wait_ring = [&]() __attribute__((always_inline)) {
       unsigned spins = 0;
       for (;;) {
         bool ok = true;
@@ -390,29 +405,60 @@ persist_kernel(const __grid_constant__ PersistMaps<MS::NS> maps, const Geom g, c
       }
       const float rt[3] = {mv[0], mv[1], mv[2]}, rb[3] = {mv[3], mv[4], mv[5]};
       write_ring(p, rt, rb);
-    }
-    // edge rows, published to the neighbours straight from registers
+    };
+    // Edge rows, published to the neighbours straight from registers.  The neighbours' rows are needed for
+    // the Laplacian only, and the Laplacian enters a cell in its last expression: on tiles whose own rows
+    // are all shown by themselves (`lazy`: every tile but a one-row last tile) the wait sits INSIDE the
+    // cell function at that point -- gates, currents and the reaction term of the edge rows are computed
+    // while the mailbox words are in flight, and receive -> publish is ring write, Laplacian, two adds.
     if (active) {
-      load_row(0);
-      load_row(TH + 1);
-      if (!plain_tile) {          // border tiles: the ring write may have refreshed rows loaded earlier
+      if (poll && !lazy) wait_ring();
+      if (!plain_tile && !lazy) {     // the ring write may have refreshed rows loaded earlier
 #pragma unroll
         for (int li = 1; li <= TH; ++li) load_row(li);
       }
+      auto outer_rows = [&]() __attribute__((always_inline)) {
+        if (poll && lazy) wait_ring();
+        load_row(0);
+        load_row(TH + 1);
+      };
       if constexpr (kPairs) {
-        do_pair(0, TH - 1, false);
+        do_pair(0, TH - 1, [&]() __attribute__((always_inline)) {
+          outer_rows();
+          return f2(lap_row(0), lap_row(TH - 1));
+        });
       } else {
-        do_row(0, false);
-        if (TH - 1 < nrows) do_row(TH - 1, false);
+        do_row(0, [&]() __attribute__((always_inline)) {
+          outer_rows();
+          return lap_row(0);
+        });
+        if (TH - 1 < nrows) do_row(TH - 1, lap_row(TH - 1));
       }
       // (the last step's rows are not consumed through the mailbox: the next launch starts from the plane)
       if (need_top) ll_store(box(want + 1, tile, 0) + c, u[0], want + 1);
       if (need_bot) ll_store(box(want + 1, tile, 1) + c, u[TH - 1], want + 1);
       write_own(p ^ 1, u, 0, TH - 1);
     }
+    if (++sub == a.period) {    // an iteration ends here
+      sub = 0;
+      if (probe_me) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < TH; ++i)
+          if (r0 + i == a.probe_row) {
+            v = u[i];
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (a.probe_var == k + 1) v = s[k][i];
+          }
+        a.ring[probe_n % FIB_PROBE_RING] = v;
+        ++probe_n;
+      }
+    }
     __syncthreads();            // shared tile of the next step complete, the old one free for reuse
     now(2 + step);
   }
+  if (probe_me) *a.ring_count = probe_n;
 
   // ---- TMA out: registers -> staging, then tile stores (rows beyond the grid are clipped)
   if (active) {

@@ -234,8 +234,8 @@ struct BeelerReuter {
   static __device__ __forceinline__ void prologue(const StepArgs<BeelerReuter>&) {}
 
   // A: anything with a member `p` of type Params (StepArgs<BeelerReuter>, or a reference wrapper)
-  template <class A, class T>
-  static __device__ __forceinline__ void cell(const A& a, T /*raw*/, T V0, T lap, T (&s)[NS], T& Vnew) {
+  template <class A, class T, class L>
+  static __device__ __forceinline__ void cell(const A& a, T /*raw*/, T V0, const L& lap, T (&s)[NS], T& Vnew) {
     const Params& p = a.p;
     const T C = s[0], M = s[1], H = s[2], J = s[3], D = s[4], F = s[5], XI = s[6];
     // every current exponential is k = e^{0.04 V0} times a constant; the exact gates reuse 1/k.
@@ -317,9 +317,10 @@ struct BeelerReuter {
     const T I_sum = vfma(gNa, V0 - T(50.0f), (iK1 + ix1) + iCa);
     // (V0 + ddt*lap) - dt*I_sum/C_m with the reference's rounding sequence (br.py:167-168): the
     // result crosses 0 mV while the operands are ~80 mV, so no FMA contraction here
-    Vnew = clip_tf(sub_rn(add_rn(V0, mul_rn(T(p.ddt), lap)), mul_rn(T(p.dt), I_sum)), -85.0f, 25.0f);
     const T dC = vfma(T(-1.0e-7f), iCa, T(0.07f) * (T(1.0e-7f) - C));
     s[0] = vfma(T(p.dt), dC, C);
+    const T reaction = mul_rn(T(p.dt), I_sum);
+    Vnew = clip_tf(sub_rn(add_rn(V0, mul_rn(T(p.ddt), lap_value<T>(lap))), reaction), -85.0f, 25.0f);
   }
 };
 

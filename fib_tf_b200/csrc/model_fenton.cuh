@@ -49,8 +49,9 @@ struct Fenton4v {
   // the pair computes exactly what the scalar cell computes and every kernel that calls this function --
   // one step per launch, two steps per launch, the persistent kernel -- agrees bit for bit.
   // A: anything with a member `p` of type Params (StepArgs<Fenton4v>, or a reference wrapper)
-  template <class A, class T>
-  static __device__ __forceinline__ void cell(const A& a, T U, T U0, T lap, T (&s)[NS], T& Unew) {
+  // L: T, or a callable returning T (lap_value, fib_math.cuh)
+  template <class A, class T, class L>
+  static __device__ __forceinline__ void cell(const A& a, T U, T U0, const L& lap, T (&s)[NS], T& Unew) {
     constexpr float tau_vp = 3.33f, tau_vn = 19.2f, tau_wp = 160.0f, tau_wn = 75.0f;
     constexpr float tau_d = 0.065f, tau_si = 31.8364f, tau_so = 31.8364f, tau_a = 0.009f;
     constexpr float u_c = 0.23f, u_m = 1.0f, u_csi = 0.8f, u_so = 0.3f;
@@ -82,10 +83,11 @@ struct Fenton4v {
 
     // (U0 + dt*dU) + ddt*lap with the reference's rounding sequence (fenton.py:103): near U ~ 0 an
     // FMA's missing rounding would show up as a 1-ulp(|U0|) absolute difference
-    Unew = add_rn(add_rn(U0, mul_rn(dt, dU)), mul_rn(T(a.p.ddt), lap));
     s[0] = vfma(dt, dV, V);
     s[1] = vfma(dt, dW, W);
     s[2] = vfma(dt, dS, S);
+    const T reaction = add_rn(U0, mul_rn(dt, dU));
+    Unew = add_rn(reaction, mul_rn(T(a.p.ddt), lap_value<T>(lap)));
   }
 
   // four cells of a thread: two packed pairs (FIB_4V_PACKED, default) or four scalar cells

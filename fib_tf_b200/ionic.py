@@ -24,9 +24,10 @@ Extra, optional config keys (all default to the reference's behaviour):
     distributed  row-shard the grid over the torch.distributed world (default False)
     lut          Courtemanche: V-only intermediates from the 150x30 table (default False)
     probe_batch  headless runs with a cl_observer: the cycle-length probe is recorded on the device
-                 every iteration and read back once per `probe_batch` iterations (default 16; the
-                 observer is then called up to that many iterations late, with the reference's
-                 arguments; 1 = read it back every iteration like the reference)
+                 every iteration and read back `probe_batch` iterations at a time, one batch behind
+                 the stepping so the device never idles (default 64; the observer is then called up
+                 to twice that many iterations late, with the reference's arguments; 1 = read it
+                 back every iteration like the reference)
 
 Collective calls under config['distributed'] (every rank must make them, in the same order):
 define(), run() (each iteration), fire_op(), image(), pot().eval() / _State[..].eval(),
@@ -301,7 +302,7 @@ class IonicModel:
         # per `probe_batch` iterations -- no host round trip per iteration.
         owner = self._row0 <= prow < self._row0 + self._rows
         ring = watch and not im and owner
-        batch = max(1, min(int(self.__dict__.get('probe_batch', 16)), _capi.PROBE_RING))
+        batch = max(1, min(int(self.__dict__.get('probe_batch', 64)), _capi.PROBE_RING // 2))
         unread = []                                              # iterations recorded, not yet read
 
         def crossing(i, v1):
@@ -315,15 +316,17 @@ class IonicModel:
                 last_spike = i
             v0 = v1
 
-        def drain():
-            vals = self._ctx.probe_fetch(len(unread)) if unread else []
-            if len(vals) != len(unread):
-                raise RuntimeError('probe ring returned %d values for %d iterations' % (len(vals), len(unread)))
+        def drain(n):
+            # the oldest n recorded iterations; the library waits only for the launch that produced
+            # them, so the iterations stepped since keep the device busy meanwhile
+            vals = self._ctx.probe_fetch(n) if n else []
+            if len(vals) != n:
+                raise RuntimeError('probe ring returned %d values for %d iterations' % (len(vals), n))
             w = self._probe_weight(prow, pcol)
-            for k, raw in zip(unread, vals):
+            for k, raw in zip(unread[:n], vals):
                 if k % plot_every == 0:
                     crossing(k, self._normalise(float(raw)) * w)
-            del unread[:]
+            del unread[:n]
 
         if ring:
             self._ctx.probe_watch(self._pot_name, prow, pcol)
@@ -333,8 +336,10 @@ class IonicModel:
                 yield i
                 if ring:
                     unread.append(i)
-                    if len(unread) >= batch:
-                        drain()
+                    if batch == 1:
+                        drain(1)
+                    elif len(unread) >= 2 * batch:
+                        drain(batch)
                 elif im and i % plot_every == 0:
                     image = self.image()
                     if self.phase is not None:
@@ -342,7 +347,7 @@ class IonicModel:
                     im.imshow(image)
                     crossing(i, image[prow, pcol])
             if ring:
-                drain()
+                drain(len(unread))
         finally:
             if ring and self._ctx is not None:
                 self._ctx.probe_watch(self._pot_name, -1, -1)

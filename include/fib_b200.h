@@ -154,8 +154,16 @@ int fib_build_lut(fib_ctx *ctx);
 int fib_court_inter(fib_ctx *ctx, const float *v_host, size_t n, float *out_host);
 
 /* ---- the hot path: replaces sess.run(self.ode_op(i)) (ionic.py:203) and
- * fire_op('slow') (ionic.py:165-169, court.py:103).  Enqueues n_iter iterations. */
+ * fire_op('slow') (ionic.py:165-169, court.py:103).  Enqueues n_iter iterations.
+ * On the persistent on-chip path (small unsharded 4v / BR grids) the iterations are only COUNTED
+ * here and launched, up to 64 per launch, by the next call on this context that observes or changes
+ * anything (state / probe / reduction reads, writes, fib_sync, the timers, fib_stream, fib_flush) or
+ * when 64 have accumulated -- results are the same, a loop of fib_step(ctx, op, 1) just costs one
+ * launch per 64 iterations.  Work enqueued on fib_stream() by the caller is ordered after everything
+ * stepped before that fib_stream() / fib_flush() call. */
 int fib_step(fib_ctx *ctx, int op, int n_iter);
+/* launch whatever fib_step has deferred (enqueue only, no synchronisation) */
+int fib_flush(fib_ctx *ctx);
 /* lock-step stepping of several shards living in ONE process (row-adjacent, ctxs[0] on top):
  * halo rows are exchanged device-to-device after every time step.  Used to emulate the
  * multi-GPU decomposition on one device and for single-process multi-GPU. */

@@ -100,7 +100,7 @@ def test_device_probe_ring_reproduces_the_per_iteration_probe(cuda):
     every, l_every, u_every = drive(probe_batch=1)
     assert ring == every and len(ring) >= 2, (ring, every)
     assert np.array_equal(u_ring, u_every)
-    assert l_ring == l_every          # same kernels; only the read-back cadence differs
+    assert l_ring <= l_every          # batched read-back lets the persistent path batch its launches too
     # the raw ring API: values in order, wrap-around, loss of the oldest
     from fib_tf_b200 import _capi
     c = _capi.Context(_capi.FENTON4V, 8, 8, 0.1, 1.0)

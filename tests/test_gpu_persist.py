@@ -1,7 +1,7 @@
-"""GPU: the persistent on-chip kernel (csrc/fib_persist.cuh) -- ONE launch per run() iteration for
-small unsharded Fenton 4v / Beeler-Reuter grids (the reference's own 512^2 configurations), state
+"""GPU: the persistent on-chip kernel (csrc/fib_persist.cuh) -- up to 64 run() iterations per launch
+for small unsharded Fenton 4v / Beeler-Reuter grids (the reference's own 512^2 configurations), state
 resident in registers / shared memory between the time steps, TMA tile loads and stores, neighbour
-tiles synchronised through release/acquire step counters.
+tiles exchanging their edge rows through a mailbox of self-validating {value, step number} words.
 
 It must reproduce one launch per time step BIT FOR BIT (same cell functions, same clamped index map,
 -fmad=false build): every model flavour, with and without a phase field, tile heights 2 / 4 / 8,
@@ -63,14 +63,15 @@ def test_fenton_persistent_kernel_is_bit_identical(cuda, H, W, th, hole):
             per.stimulate(*stim)
             ref.stimulate(*stim)
     per.step(0, 3)
+    per.flush()                              # iterations are deferred until something looks (include/fib_b200.h)
     assert 'persist_kernel<Fenton4v,TH=%d,PHASE=%d>' % (th, hole) in _capi.last_kernel(), _capi.last_kernel()
     ref.step(0, 3)
     for v in ref.var_names:
         want = ref.get_state(v)
         assert np.isfinite(want).all()
         assert np.array_equal(per.get_state(v), want), v
-    # ONE launch per fib_step call: four single iterations + three iterations in one launch (+ the stimulus)
-    assert per.launch_count() - n_per == 4 + 1 + 1 and ref.launch_count() - n_ref == 70 + 1
+    # deferred iterations: two before the stimulus in one launch, the five after it in another (+ the stimulus)
+    assert per.launch_count() - n_per == 2 + 1 and ref.launch_count() - n_ref == 70 + 1
     per.close()
     ref.close()
 
@@ -100,6 +101,7 @@ def test_beeler_reuter_persistent_kernel_is_bit_identical(cuda, H, W, th, hole, 
             per.stimulate(*stim)
             ref.stimulate(*stim)
     per.step(0, 1)
+    per.flush()
     name = {'exact': 'exact', 'cheby': 'cheby'}['cheby' if 'cheby' in flags else 'exact']
     if 'strict' in flags:
         name = 'strict'
@@ -109,7 +111,7 @@ def test_beeler_reuter_persistent_kernel_is_bit_identical(cuda, H, W, th, hole, 
     for v in ref.var_names:
         a, b = per.get_state(v), ref.get_state(v)
         assert np.array_equal(a, b, equal_nan=True), (v, float(np.nanmax(np.abs(a - b))))
-    assert per.launch_count() - n_per == 6 + 1 and ref.launch_count() - n_ref == 30 + 1
+    assert per.launch_count() - n_per == 2 + 1 and ref.launch_count() - n_ref == 30 + 1
     per.close()
     ref.close()
 
@@ -142,3 +144,50 @@ def test_persistent_kernel_is_not_used_where_it_does_not_apply(cuda):
         m.close()
     assert np.array_equal(states[0], states[1])
     assert [s[1:] for s in seen if s[0]] == [s[1:] for s in seen if not s[0]] and seen
+
+
+@pytest.mark.parametrize('model,watch', [('4v', 'U'), ('4v', 'W'), ('br', 'V'), ('br', 'XI')])
+def test_deferred_iterations_and_the_in_kernel_probe_ring(cuda, model, watch):
+    """fib_step on the persistent path only counts; the launch (up to 64 iterations, the watched cell
+    recorded by the kernel itself after every iteration) happens when something looks.  The ring and the
+    state must be those of one launch per step with probe_record_kernel between the iterations."""
+    from fib_tf_b200 import _capi
+    H, W = 200, 160
+    rng = np.random.default_rng(11)
+    if model == '4v':
+        init = {v: rng.uniform(0.0, 1.0, (H, W)).astype(np.float32) for v in ('U', 'V', 'W', 'S')}
+        per, ref = _pair(_capi.FENTON4V, H, W, 0.1, 1.5, 0, init, _phase(H, W), None)
+        stim = ('U', 90, 110, 70, 90, 0.5, 0.0)
+    else:
+        init = {'V': rng.uniform(-85.0, 20.0, (H, W)).astype(np.float32),
+                'C': rng.uniform(5e-5, 5e-3, (H, W)).astype(np.float32)}
+        for g in ('M', 'H', 'J', 'D', 'F', 'XI'):
+            init[g] = rng.uniform(1e-3, 0.998, (H, W)).astype(np.float32)
+        per, ref = _pair(_capi.BR, H, W, 0.1, 0.809, _capi.F_SKIP, init, None, None)
+        stim = ('V', 90, 110, 70, 90, 10.0, -90.0)
+    for c in (per, ref):
+        c.probe_watch(watch, 101, 77)            # row 101 is not the first row of its tile
+    n0 = per.launch_count()
+    for it in range(150):
+        per.step(0, 1)
+        ref.step(0, 1)
+        if it == 99:
+            per.stimulate(*stim)                 # covers the probe cell: updates the last record
+            ref.stimulate(*stim)
+    a, b = per.probe_fetch(), ref.probe_fetch()
+    assert a.size == 150 and np.array_equal(a, b)
+    # 64 + 36 iterations before the stimulus, 50 after it: three step launches (+ stimulus + record update)
+    assert per.launch_count() - n0 <= 3 + 2
+    per.step(0, 3)
+    ref.step(0, 3)
+    assert np.array_equal(per.probe_fetch(), ref.probe_fetch())
+    # partial fetches wait for the launch that produced the values asked for, not for the whole stream
+    for it in range(130):
+        per.step(0, 1)
+        ref.step(0, 1)
+    a = np.concatenate([per.probe_fetch(64), per.probe_fetch(10), per.probe_fetch()])
+    assert a.size == 130 and np.array_equal(a, ref.probe_fetch())
+    for v in ref.var_names:
+        assert np.array_equal(per.get_state(v), ref.get_state(v)), v
+    per.close()
+    ref.close()

@@ -131,7 +131,7 @@ def test_run_generator_order_and_stimulus_rectangle(recording):
 
 
 def test_cycle_length_observer_without_a_screen(recording):
-    m = BeelerReuter(dict(CFG, duration=30, dt_per_plot=5))     # probe every iteration (5/5)
+    m = BeelerReuter(dict(CFG, duration=30, dt_per_plot=5, probe_batch=16))     # probe every iteration (5/5)
     m.define()
     hits = []
     m.cl_observer = lambda i, cl: hits.append((i, cl))
@@ -141,10 +141,11 @@ def test_cycle_length_observer_without_a_screen(recording):
         pass
     assert [h[0] for h in hits] == [4, 40]
     assert hits[1][1] == pytest.approx((40 - 4) * 5 * 0.1)        # cycle length in ms (ionic.py:218)
-    # the probe cell [20, W//2] is watched on the device and read back in batches of 16 iterations
+    # the probe cell [20, W//2] is watched on the device and read back 16 iterations at a time, one batch
+    # behind the stepping (at iterations 31 and 47), the rest at the end
     calls = m._ctx.calls
     assert ('watch', 'V', 20, 32) in calls and not [c for c in calls if c[0] == 'probe']
-    assert [c[1] for c in calls if c[0] == 'fetch'] == [16, 16, 16, 12]
+    assert [c[1] for c in calls if c[0] == 'fetch'] == [16, 16, 28]
     assert calls[-2] == ('watch', 'V', -1, -1)
     # probe_batch = 1: read back after every iteration, same observer calls
     m = BeelerReuter(dict(CFG, duration=30, dt_per_plot=5, probe_batch=1))
