@@ -98,17 +98,18 @@ def pinned_strips(tile, width):
 
 def upload_tiled(ctx, strips, row0, rows, width):
     """Strip-wise H2D upload (from pinned memory) of the mirror-tiled state for global rows
-    [row0, row0+rows): every 512-row block of every plane is one ENQUEUE-ONLY fib_set_rect_async
-    (no host round trip per strip; the copies are ordered before the first step on the stream)."""
+    [row0, row0+rows): every 512-row strip of every plane is one ENQUEUE-ONLY fib_set_rect_async, issued
+    top to bottom with all planes of a strip together, so that on an unsharded grid the library can step
+    block by block behind the copies (csrc/fib_capi.cu finish_upload_session)."""
     nbytes = 0
-    for name, pinned in strips.items():
-        g = row0
-        while g < row0 + rows:
-            t, r = divmod(g, TILE)
-            n = min(TILE - r, row0 + rows - g)
+    g = row0
+    while g < row0 + rows:
+        t, r = divmod(g, TILE)
+        n = min(TILE - r, row0 + rows - g)
+        for name, pinned in strips.items():
             ctx.set_rect_async(name, g, 0, pinned[t & 1][r:r + n])
             nbytes += n * width * 4
-            g += n
+        g += n
     return nbytes
 
 
@@ -457,8 +458,8 @@ def main():
     h2d = upload_tiled(ctx, strips, row0, rows, size)
     with contextlib.redirect_stdout(sys.stderr):
         for i in model.run(None):
-            if i % 10 == 0:                               # frame grab cadence of fenton.py:184
-                if i:
+            if i % 10 == 9:                               # a frame every 10 iterations (fenton.py:184)
+                if i > 9:
                     model.image_wait()
                 model.image_async(frame)                  # pinned target, overlaps the next steps
                 d2h += frame.nbytes

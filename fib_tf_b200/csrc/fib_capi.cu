@@ -150,6 +150,19 @@ struct fib_ctx {
   unsigned long long* pmail = nullptr;   // edge-row mailbox of the persistent kernel, words {value, step number}
   unsigned pbase = 0;
   int pending = 0;                    // ODE iterations accepted by fib_step but not launched yet (see flush_pending)
+  // Pipelined upload (fib_set_rect_async of full-width row blocks, top to bottom, every plane): the copies
+  // run on their own stream; `arrivals` = {rows [row0, row_end) of EVERY plane are enqueued up to `ev`}.
+  // Iterations stepped while such a session is open are deferred and then run block by block behind the
+  // copies (finish_upload_session).
+  struct Arrival { int row_end; cudaEvent_t ev; };
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t ev_up_begin = nullptr;
+  bool up_session = false;
+  std::vector<Arrival> arrivals;
+  std::vector<int> up_front;          // per plane: rows [row0, up_front) enqueued
+  std::vector<cudaEvent_t> ev_pool;
+  long long pipeline_min_cells = 1ll << 22;   // smaller grids: not worth it (FIB_PIPELINE_MIN_CELLS)
+  int pipeline_block_rows = 1024;             // rows per block of the skewed schedule, at least (FIB_PIPELINE_BLOCK_ROWS)
   int* perr = nullptr;                // page-locked, device-visible: raised by a timed-out neighbour wait
   unsigned long long* ptimeline = nullptr;   // page-locked [16], FIB_PERSIST_TIMELINE=1 only
   CUtensorMap pmap_x[2], pmap_s[8];
@@ -449,6 +462,10 @@ static int create_resources(fib_ctx* c) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_up_begin, cudaEventDisableTiming));
+  if (const char* e = getenv("FIB_PIPELINE_MIN_CELLS")) c->pipeline_min_cells = atoll(e);
+  if (const char* e = getenv("FIB_PIPELINE_BLOCK_ROWS")) c->pipeline_block_rows = max(atoi(e), 1);
   CU(cudaEventCreateWithFlags(&c->ev_snap_ready, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_start));
@@ -491,6 +508,13 @@ extern "C" int fib_destroy(fib_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->up_stream) {
+    cudaStreamSynchronize(c->up_stream);
+    cudaStreamDestroy(c->up_stream);
+  }
+  if (c->ev_up_begin) cudaEventDestroy(c->ev_up_begin);
+  for (auto& a : c->arrivals) cudaEventDestroy(a.ev);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaFree(c->snap);
   if (c->ev_snap_ready) cudaEventDestroy(c->ev_snap_ready);
   if (c->ev_snap_done) cudaEventDestroy(c->ev_snap_done);
@@ -579,7 +603,7 @@ static cudaError_t wait_comm(fib_ctx* c) {
 static int flush_pending(fib_ctx* c);
 #define FLUSH(c)                                                      \
   do {                                                                \
-    if ((c)->pending) {                                               \
+    if ((c)->pending || (c)->up_session) {                            \
       const int fr_ = flush_pending(c);                               \
       if (fr_) return fr_;                                            \
     }                                                                 \
@@ -664,20 +688,90 @@ extern "C" int fib_snapshot_wait(fib_ctx* c) {
   return 0;
 }
 
+// the probe ring's storage (allocations may synchronise with copies in flight: never between the
+// blocks of a pipelined upload and the steps behind it)
+static int ensure_ring(fib_ctx* c) {
+  if (!c->ring) {
+    CU(cudaHostAlloc(&c->ring, FIB_PROBE_RING * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+    CU(cudaMalloc(&c->ring_count, sizeof(unsigned long long)));
+  }
+  for (int k = 0; k < fib_ctx::kRingEvents; ++k)
+    if (!c->ring_ev[k]) CU(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
+  return 0;
+}
+
+static int launch_substep(fib_ctx* c, int op, int sub, int lr0, int nrows);
+static int substeps_of(const fib_ctx* c, int op);
+// Everything an ODE iteration and its probe record can launch is loaded NOW (lazy loading would do it at
+// the first launch and wait for the copies in flight).  Called when a pipelined upload begins.
+static int preload_kernels(fib_ctx* c) {
+  int r = ensure_ring(c);
+  if (r) return r;
+  cudaFuncAttributes fa;
+  CU(cudaFuncGetAttributes(&fa, probe_record_kernel));
+  CU(cudaFuncGetAttributes(&fa, probe_update_kernel));
+  const uint64_t l0 = c->launches;
+  preload_only() = true;
+  const int ns = substeps_of(c, FIB_OP_ODE);
+  for (int s = 0; s < ns && !r; s += c->fuse)
+    for (int nrows : {c->g.rows, min(c->g.rows, c->pipeline_block_rows)})
+      if (!r) r = launch_substep(c, FIB_OP_ODE, s, 0, nrows);
+  preload_only() = false;
+  c->launches = l0;
+  cudaGetLastError();
+  return 0;       // best effort: a model that cannot step yet (table not set) reports that from fib_step
+}
+
 static int set_rect_impl(fib_ctx* c, int var, int r0, int r1, int c0, int c1, const float* host, bool sync) {
   if (!c || !host) return fail(FIB_E_ARG, "ctx/host is NULL");
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   if (r0 < c->g.row0 || r1 > c->g.row0 + c->g.rows || r0 >= r1 || c0 < 0 || c1 > c->g.W || c0 >= c1)
     return fail(FIB_E_ARG, "rectangle [%d,%d)x[%d,%d) not inside this shard", r0, r1, c0, c1);
   DevGuard dg(c->cfg.device);
-  FLUSH(c);
   if (!sync) {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
       cudaGetLastError();
       return fail(FIB_E_ARG, "fib_set_rect_async needs page-locked host memory (fib_host_alloc)");
     }
+    // A full-width block that continues this plane's upload frontier (or starts one at the first row) of a
+    // large unsharded grid goes to the upload stream: iterations stepped before anything looks at the
+    // result then run block by block BEHIND the copies instead of after them (finish_upload_session).
+    const bool eligible = !c->comm && c->g.rows == c->g.H && c0 == 0 && c1 == c->g.W && c->watch_var < 0 &&
+                          (long long)c->g.rows * c->g.W >= c->pipeline_min_cells;
+    if (eligible && !c->pending && (c->up_session ? r0 == c->up_front[var] : r0 == c->g.row0)) {
+      if (!c->up_session) {
+        const int pr = preload_kernels(c);
+        if (pr) return pr;                                       // (allocation failures only)
+        CU(cudaEventRecord(c->ev_up_begin, c->stream));          // after everything stepped so far
+        CU(cudaStreamWaitEvent(c->up_stream, c->ev_up_begin, 0));
+        if (c->snap_pending) CU(cudaStreamWaitEvent(c->up_stream, c->ev_snap_done, 0));
+        c->up_front.assign(c->nvars, c->g.row0);
+        c->up_session = true;
+      }
+      float* dst = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch;
+      CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)c->g.W * sizeof(float),
+                           (size_t)c->g.W * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, c->up_stream));
+      c->up_front[var] = r1;
+      int done = r1;
+      for (int f : c->up_front) done = min(done, f);
+      const int had = c->arrivals.empty() ? c->g.row0 : c->arrivals.back().row_end;
+      if (done - had >= c->pipeline_block_rows || (done > had && done == c->g.row0 + c->g.rows)) {
+        cudaEvent_t ev = nullptr;
+        if (!c->ev_pool.empty()) {
+          ev = c->ev_pool.back();
+          c->ev_pool.pop_back();
+        } else {
+          CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(ev, c->up_stream));
+        c->arrivals.push_back({done, ev});
+      }
+      if (var == 0 || c->fuse == 2) c->halo_dirty = true;
+      return 0;
+    }
   }
+  FLUSH(c);
   CU(wait_comm(c));
   float* dst = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch + c0;
   CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)(c1 - c0) * sizeof(float),
@@ -1352,9 +1446,56 @@ static int step_now(fib_ctx* c, int op, int n_iter) {
   return 0;
 }
 
+// Ends a pipelined upload (see set_rect_impl) and runs the `n` ODE iterations deferred meanwhile.
+// With blocks ending at rows a_0 < a_1 < .. < a_m = H and nb rows of halo per launch, launch l of block j
+// covers rows [a_{j-1} - nb (l+1), a_j - nb (l+1)) (first block from row 0, last block to row H): every row
+// gets every launch exactly once and in order, a launch reads only rows its predecessors have brought to
+// its time level, and block j's launches wait for block j's copies only -- the same arithmetic on the
+// same values as stepping after the whole upload, so the result is bit-identical.
+static int finish_upload_session(fib_ctx* c, int n) {
+  c->up_session = false;
+  std::vector<fib_ctx::Arrival> blocks;
+  blocks.swap(c->arrivals);
+  auto release = [&]() {
+    for (auto& b : blocks) c->ev_pool.push_back(b.ev);
+  };
+  const int op = FIB_OP_ODE;
+  const int nb = c->fuse, nl = substeps_of(c, op) / c->fuse, L = n * nl;
+  const int row0 = c->g.row0, rows = c->g.rows;
+  bool skew = n > 0 && blocks.size() > 1 && blocks.back().row_end == row0 + rows && c->persist != 1 &&
+              blocks[0].row_end - row0 > nb * (L + 2);
+  for (size_t j = 1; skew && j < blocks.size(); ++j) skew = blocks[j].row_end - blocks[j - 1].row_end > 2 * nb;
+  if (!skew) {
+    if (!blocks.empty()) CU(cudaStreamWaitEvent(c->stream, blocks.back().ev, 0));
+    release();
+    return n ? step_now(c, op, n) : 0;
+  }
+  const int cur0 = c->cur;
+  const bool flips = op_writes_x(c, op);
+  int r = 0;
+  for (size_t j = 0; j < blocks.size() && !r; ++j) {
+    CU(cudaStreamWaitEvent(c->stream, blocks[j].ev, 0));
+    const bool last = j + 1 == blocks.size();
+    for (int l = 0; l < L && !r; ++l) {
+      const int lo = j == 0 ? 0 : blocks[j - 1].row_end - row0 - nb * (l + 1);
+      const int hi = last ? rows : blocks[j].row_end - row0 - nb * (l + 1);
+      c->cur = cur0 ^ ((flips && (l & 1)) ? 1 : 0);
+      r = launch_substep(c, op, (l % nl) * c->fuse, lo, hi - lo);
+      if (!r && (l + 1) % nl == 0 && c->watch_var >= 0 && c->watch_row - row0 >= lo && c->watch_row - row0 < hi) {
+        if (flips) c->cur ^= 1;
+        r = record_probe(c, op);        // the watched cell's row has finished this iteration
+      }
+    }
+  }
+  c->cur = cur0 ^ ((flips && (L & 1)) ? 1 : 0);
+  release();
+  return r;
+}
+
 static int flush_pending(fib_ctx* c) {
   const int n = c->pending;
   c->pending = 0;
+  if (c->up_session) return finish_upload_session(c, n);
   return n ? step_now(c, FIB_OP_ODE, n) : 0;
 }
 
@@ -1367,6 +1508,16 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
   if (!c->comm && c->g.rows != c->g.H)
     return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
   if (!c->comm && c->persist < 0) decide_persist(c);
+  if (c->up_session && op == FIB_OP_ODE && c->persist != 1 && !c->arrivals.empty()) {
+    // an upload is still in flight: count the iterations, run them behind the copies when something looks
+    // (finish_upload_session); at most as many as the first block's height allows
+    const int nl = substeps_of(c, op) / c->fuse;
+    const int room = (c->arrivals[0].row_end - c->g.row0) / c->fuse - 2 - (c->pending + n_iter) * nl;
+    if (room > 0) {
+      c->pending += n_iter;
+      return 0;
+    }
+  }
   if (c->persist == 1 && op == FIB_OP_ODE && !c->ptimeline) {
     // persistent path: count now, launch later (see FLUSH); whatever can fail is checked here
     if (c->cfg.model == FIB_BR && (c->cfg.flags & FIB_F_CHEBY) && !c->have_cheb)
@@ -1597,7 +1748,7 @@ static void drop_graphs(fib_ctx* c) {
 extern "C" int fib_probe_watch(fib_ctx* c, int var, int row, int col) {
   if (!c) return fail(FIB_E_ARG, "ctx is NULL");
   DevGuard dg(c->cfg.device);
-  FLUSH(c);
+  if (c->pending) FLUSH(c);             // (an upload still in flight stays in flight: nothing is read here)
   CU(cudaStreamSynchronize(c->stream));
   drop_graphs(c);                       // the record node is part of the iteration graph
   if (row < 0) {
@@ -1607,16 +1758,13 @@ extern "C" int fib_probe_watch(fib_ctx* c, int var, int row, int col) {
   if (var < 0 || var >= c->nvars) return fail(FIB_E_ARG, "state variable %d out of range", var);
   if (row < c->g.row0 || row >= c->g.row0 + c->g.rows || col < 0 || col >= c->g.W)
     return fail(FIB_E_ARG, "probe (%d,%d) is not in this shard", row, col);
-  if (!c->ring) {
-    CU(cudaHostAlloc(&c->ring, FIB_PROBE_RING * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
-    CU(cudaMalloc(&c->ring_count, sizeof(unsigned long long)));
+  {
+    const int er = ensure_ring(c);
+    if (er) return er;
   }
   CU(cudaMemsetAsync(c->ring_count, 0, sizeof(unsigned long long), c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < fib_ctx::kRingEvents; ++k) {
-    if (!c->ring_ev[k]) CU(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
-    c->ring_ev_total[k] = 0;
-  }
+  for (int k = 0; k < fib_ctx::kRingEvents; ++k) c->ring_ev_total[k] = 0;
   c->ring_total = 0;
   c->ring_fetched = 0;
   c->watch_var = var;

@@ -252,6 +252,11 @@ inline cudaError_t launch_fused2(const Geom& g, Fused2Args a, cudaStream_t st, i
   }
   a.R = R;
   dim3 block(kBX, BY), grid((unsigned)nseg, (unsigned)(((a.nrows + R - 1) / R + BY - 1) / BY));
+  if (preload_only()) {
+    cudaFuncAttributes fa;
+    return a.phase ? cudaFuncGetAttributes(&fa, fenton_fused2_kernel<true>)
+                   : cudaFuncGetAttributes(&fa, fenton_fused2_kernel<false>);
+  }
   snprintf(last_kernel_name(), 160, "fenton_fused2_kernel<PHASE=%d>,R=%d", a.phase ? 1 : 0, R);
   if (a.phase) fenton_fused2_kernel<true><<<grid, block, 0, st>>>(g, a);
   else fenton_fused2_kernel<false><<<grid, block, 0, st>>>(g, a);

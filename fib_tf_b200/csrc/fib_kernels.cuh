@@ -62,6 +62,13 @@ inline bool& pdl_enabled() {
   static thread_local bool on = true;
   return on;
 }
+// Set around a launch wrapper: do not launch, only make sure the kernel is LOADED (the runtime loads
+// kernels lazily on first use, and that load waits for copies in flight -- fatal for the pipelined
+// upload, whose whole point is to launch behind them; see preload_kernels in fib_capi.cu)
+inline bool& preload_only() {
+  static thread_local bool on = false;
+  return on;
+}
 // the flavour launched last on this thread (fib_last_kernel): tests use it to prove which
 // instantiation -- cells per thread, marching depth -- they compared with the oracle
 inline char* last_kernel_name() {
@@ -203,6 +210,10 @@ inline cudaError_t launch_step_r(const Geom& g, const StepArgs<M>& a, cudaStream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (FIB_NC_LOADS == 0 && pdl && pdl_enabled()) ? 1 : 0;   // see fib_common.cuh
+  if (preload_only()) {
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, step_kernel<M, VEC, R, BY, PHASE>);
+  }
   snprintf(last_kernel_name(), 160, "step_kernel<%s,VEC=%d,R=%d,BY=%d,PHASE=%d>", M::name(), VEC, R, BY,
            PHASE ? 1 : 0);
   return cudaLaunchKernelEx(&cfg, step_kernel<M, VEC, R, BY, PHASE>, g, a);

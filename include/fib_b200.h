@@ -125,7 +125,14 @@ int fib_get_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, float *h
 int fib_set_rect(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host);
 /* enqueue-only variant of fib_set_rect: `host_pinned` (page-locked, fib_host_alloc) must stay valid and
  * unchanged until the next fib_sync / synchronous call; the copy is ordered before every later call on
- * this context.  Lets a caller stream a large initial state strip by strip without a round trip each. */
+ * this context.  Lets a caller stream a large initial state strip by strip without a round trip each.
+ * Pipelined upload: full-width blocks of a large unsharded grid, enqueued top to bottom with every plane
+ * of a block before the next block, are copied on a stream of their own, and ODE iterations stepped
+ * before anything reads or writes the state run block by block BEHIND the copies -- launch l of the block
+ * ending at row a covers rows [a' - h(l+1), a - h(l+1)) (a' = end of the block above, h = time steps per
+ * launch), so every launch reads only rows already at its time level.  Same arithmetic on the same
+ * values: the result is bit-identical to copying everything first (tests/test_gpu_pipelined_upload.py);
+ * the 16 GiB upload of the 32768^2 benchmark state hides behind the first ten iterations. */
 int fib_set_rect_async(fib_ctx *ctx, int var, int r0, int r1, int c0, int c1, const float *host_pinned);
 
 /* asynchronous frame grab (the cube.npy writer of fenton.py:179-187 without stalling the stepper):
