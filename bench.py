@@ -458,8 +458,8 @@ def main():
     h2d = upload_tiled(ctx, strips, row0, rows, size)
     with contextlib.redirect_stdout(sys.stderr):
         for i in model.run(None):
-            if i % 10 == 9:                               # a frame every 10 iterations (fenton.py:184)
-                if i > 9:
+            if i % 10 == 9 or i == K - 1:                 # a frame every 10 iterations (fenton.py:184) + the last
+                if d2h:
                     model.image_wait()
                 model.image_async(frame)                  # pinned target, overlaps the next steps
                 d2h += frame.nbytes

@@ -490,7 +490,9 @@ class IonicModel:
 
     def image_wait(self):
         self._ctx.snapshot_wait()
-        a = self._snap
+        a = getattr(self, '_snap', None)
+        if a is None:
+            raise RuntimeError('image_wait() without a preceding image_async()')
         return a if self.MODEL_ID == _capi.FENTON4V else self._normalise(a)
 
     def sync(self):

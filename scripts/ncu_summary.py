@@ -28,22 +28,31 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio']
-CELLS = 4096 * 4096
 traffic = {}
 lines = []
 # (report, key in traffic.json, algorithmic bytes per cell-step, time steps per launch)
-for rep, key, balg, spl in (('prof_4v', 'fenton4v_step', 32, 1), ('prof_4v_fused', 'fenton4v_fused2_step', 32, 2),
-                            ('prof_br', 'br_cheby_step', 64, 1), ('prof_br_exact', 'br_exact_step', 64, 1),
-                            ('prof_court', 'court_ultra_step', 168, 1)):
+# (the persistent kernel: one launch = 64 iterations of a 512^2 grid, state on chip in between)
+for rep, key, balg, spl, CELLS in (
+        ('prof_4v', 'fenton4v_step', 32, 1, 4096 * 4096), ('prof_4v_fused', 'fenton4v_fused2_step', 32, 2, 4096 * 4096),
+        ('prof_br', 'br_cheby_step', 64, 1, 4096 * 4096), ('prof_br_exact', 'br_exact_step', 64, 1, 4096 * 4096),
+        ('prof_court', 'court_ultra_step', 168, 1, 4096 * 4096),
+        ('prof_court_lut', 'court_lut_step', 168, 1, 4096 * 4096),
+        ('prof_persist_4v', 'fenton4v_persist_512', 32, 640, 512 * 512),
+        ('prof_persist_br', 'br_cheby_persist_512', 64, 320, 512 * 512)):
     path = os.path.join(G, rep + '.ncu-rep')
-    if not os.path.exists(path):
+    pre = os.path.join(G, rep + '.raw.csv')          # exported on the GPU box (scripts/gpu_ncu.sh)
+    if os.path.exists(pre) and os.path.getsize(pre) > 0:
+        txt = open(pre).read()
+    elif os.path.exists(path):
+        txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, r = rows[0], rows[1], rows[2]
     d = {h: (r[i], units[i]) for i, h in enumerate(hdr)}
-    lines.append('== %s : %s   (4096x4096 grid, one launch = %s, ncu --set full --clock-control none)'
-                 % (rep, d['Kernel Name'][0], 'one time step' if spl == 1 else '%d time steps' % spl))
+    side = int(round(CELLS ** 0.5))
+    lines.append('== %s : %s   (%dx%d grid, one launch = %s, ncu --set full --clock-control none)'
+                 % (rep, d['Kernel Name'][0], side, side, 'one time step' if spl == 1 else '%d time steps' % spl))
     for k in KEEP:
         if k in d:
             lines.append('   %-86s %s %s' % (k, d[k][0], d[k][1]))
@@ -72,9 +81,9 @@ if os.path.exists(lp):
             agg[r[4]][0] += 1
             agg[r[4]][1] += float(r[-1])
     tot = sum(v[1] for v in agg.values())
-    lines.append('== launch list of `python bench.py --size 4096 --steps 2 --warmup 3 --no-cpu` '
-                 '(ncu --metrics gpu__time_duration.sum --launch-skip 4011 --launch-count 60: the warm-up tail, the timed '
-                 'region and the e2e loop, after the 4000 launches that build the 512^2 spiral tile; shares, not absolutes)')
+    lines.append('== launch list of `python bench.py --size 4096 --steps 2 --warmup 3 --no-cpu --no-suite` '
+                 '(ncu --metrics gpu__time_duration.sum, every launch of the run: the persistent kernel building the '
+                 '512^2 spiral tile, the warm-up, the timed region, the e2e loop; shares, not absolutes)')
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append('   %5.1f %%  %4d launches  %9.1f us avg   %s' % (100 * ns / tot, n, ns / n / 1e3, k[:90]))
 open(os.path.join(OUT, '%s_ncu_summary.txt' % tag), 'w').write('\n'.join(lines) + '\n')
