@@ -270,7 +270,7 @@ def run_reference_arm(args):
                 'TensorFlow is not installable offline); each step is one run() iteration of a '
                 'bounded 2048^2 sample of the workload; no GPU and no product code is touched',
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(size, n):
@@ -361,7 +361,27 @@ def run_suite(device, peak, budget_s=45.0):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON: everything else any library prints there (NCCL's version
+    banner, for one) is sent to stderr by pointing fd 1 at fd 2 for the life of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -523,7 +543,7 @@ def main():
         info['numpy_restatement'] = numpy_restatement_baseline()
         line['cpu_baseline'] = info
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     for p in [b for bufs in strips.values() for b in bufs] + [frame]:
         _capi.pinned_free(p)
     model.close()

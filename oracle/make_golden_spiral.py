@@ -10,6 +10,10 @@ S2 'luq' at 210 ms, 1000 ms) and br.py:347-382 (BR 512^2, cheby=True, hole (150,
     python oracle/make_golden_spiral.py fenton      -> tests/golden/spiral_fenton.npz
     python oracle/make_golden_spiral.py br          -> tests/golden/spiral_br.npz
     python oracle/make_golden_spiral.py court | court_ultra   (700 ms, court.py / court_ultra.py loops)
+    python oracle/make_golden_spiral.py <which> --alt   -> tests/golden/spiral_<which>_alt.npz: the same run
+        with the facade's transcendental functions swapped for another correctly rounding library
+        (tfshim.ALT_LIBM), probes only -- how far the REFERENCE ITSELF moves in cycle length / APD
+        when nothing but its math library changes (the floor for any statistical bound)
 
 Stored: the transmembrane variable at PROBES after every run() iteration ([samples, n_probes] fp32)
 and 64x64 block-subsampled frames every 50 ms -- enough to compare rotation period, APD and
@@ -37,7 +41,8 @@ warnings.simplefilter('ignore')
 PROBES = [(20, 256), (128, 128), (128, 384), (384, 128), (384, 384), (256, 400), (400, 256), (60, 60)]
 
 
-def main(which):
+def main(which, alt=False):
+    shim.ALT_LIBM = bool(alt)
     if which == 'fenton':
         import fenton
         cfg = {'width': 512, 'height': 512, 'dt': 0.1, 'dt_per_plot': 10, 'diff': 1.5, 'duration': 1000,
@@ -93,11 +98,16 @@ def main(which):
             'dt_per_step': model.dt_per_step, 'probes': PROBES, 'frame_every_iter': every,
             'generator': 'oracle/make_golden_spiral.py (unmodified reference under oracle/tfshim.py)',
             'seconds': time.time() - t0}
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'spiral_%s.npz' % which),
-                        meta=np.array(json.dumps(meta)), probes=np.asarray(trace, np.float32),
-                        frames=np.asarray(frames, np.float32))
+    if alt:
+        meta['generator'] += ', tfshim.ALT_LIBM = True'
+        np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'spiral_%s_alt.npz' % which),
+                            meta=np.array(json.dumps(meta)), probes=np.asarray(trace, np.float32))
+    else:
+        np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'spiral_%s.npz' % which),
+                            meta=np.array(json.dumps(meta)), probes=np.asarray(trace, np.float32),
+                            frames=np.asarray(frames, np.float32))
     print('%s done in %.0f s' % (which, time.time() - t0))
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    main(sys.argv[1], alt='--alt' in sys.argv[2:])
