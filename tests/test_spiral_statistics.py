@@ -15,9 +15,12 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-# mean cycle length / mean APD after S2, relative (measured values: profiles/r2_spiral_report.txt)
-CL_BOUND = 0.02
-APD_BOUND = 0.02
+# Bounds, relative (round 2: 1 %, was 2-3 %).  profiles/r2_spiral_report.txt lists what is measured per probe --
+# 4v / BR / court_ultra agree with the reference to <= 0.03 %, court.py to <= 0.52 % in APD -- next to how far the
+# UNMODIFIED reference moves when only its math library is swapped (tests/golden/spiral_*_alt.npz,
+# scripts/spiral_spread.py: <= 0.01 % for 4v, 0.9 % in APD / 0.45 ms in activation time for court.py).
+CL_BOUND = 0.01
+APD_BOUND = 0.01
 
 
 def load(which):
@@ -106,7 +109,7 @@ def test_spiral_run_matches_the_reference_statistically(cuda_device, which):
             compared += 1
         elif len(up_r) == len(up_c) and len(up_r) >= 2:
             # few beats in the window (Courtemanche, 700 ms): compare them one by one
-            assert np.all(np.abs(up_c - up_r) <= 0.01 * up_r + 1.0), ('activation times', k, up_c, up_r)
+            assert np.all(np.abs(up_c - up_r) <= 0.001 * up_r + 0.5), ('activation times', k, up_c, up_r)
             a_r, a_c = apds(up_r, dn_r), apds(up_c, dn_c)
             n = min(len(a_r), len(a_c))
             report.append('%s probe %d (beat by beat): activation times off by <= %.3f ms (%.3f %%), APD off by <= %.3f ms '
@@ -114,17 +117,22 @@ def test_spiral_run_matches_the_reference_statistically(cuda_device, which):
                                                    100 * np.max(np.abs(up_c - up_r) / up_r),
                                                    np.max(np.abs(a_c[:n] - a_r[:n])) if n else 0.0,
                                                    100 * np.max(np.abs(a_c[:n] - a_r[:n]) / a_r[:n]) if n else 0.0, len(up_r)))
-            assert len(a_r) == len(a_c) and np.all(np.abs(a_c - a_r) <= 0.03 * a_r + 0.5), ('APD', k, a_c, a_r)
+            assert len(a_r) == len(a_c) and np.all(np.abs(a_c - a_r) <= APD_BOUND * a_r), ('APD', k, a_c, a_r)
             compared += 1
+    n_pre = int(meta['s2_iter'] // meta['frame_every_iter'])
+    pre_err = float(np.max(np.abs(frames[:n_pre] - ref_frames[:n_pre]))) / (hi - lo)
+    frac_err = max([abs(float((f_c > level).mean()) - float((f_r > level).mean()))
+                    for f_c, f_r in zip(frames[n_pre + 2:], ref_frames[n_pre + 2:])] or [0.0])
+    report.append('%s frames: before S2 point-wise within %.4f %% of the range, afterwards excited fraction within %.5f'
+                  % (which, 100 * pre_err, frac_err))
     if os.environ.get('FIB_SPIRAL_REPORT'):
         with open(os.environ['FIB_SPIRAL_REPORT'], 'a') as f:
             f.write('\n'.join(report) + '\n')
     assert compared >= 3, 'too few probes could be compared'
-    # frames before S2 agree point-wise (1 % of range); afterwards the excited fraction agrees
-    n_pre = int(meta['s2_iter'] // meta['frame_every_iter'])
-    assert np.max(np.abs(frames[:n_pre] - ref_frames[:n_pre])) <= 0.01 * (hi - lo) * 5
-    for f_c, f_r in zip(frames[n_pre + 2:], ref_frames[n_pre + 2:]):
-        assert abs((f_c > level).mean() - (f_r > level).mean()) <= 0.05
+    # frames before S2 agree point-wise (a steep front shifted by a fraction of a step: 5 % of the range);
+    # afterwards the excited fraction agrees
+    assert pre_err <= 0.05, pre_err
+    assert frac_err <= 0.01, frac_err
 
 
 def test_lookup_table_flavour_tracks_the_exact_model(cuda_device):
