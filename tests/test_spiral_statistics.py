@@ -129,9 +129,9 @@ def test_spiral_run_matches_the_reference_statistically(cuda_device, which):
         with open(os.environ['FIB_SPIRAL_REPORT'], 'a') as f:
             f.write('\n'.join(report) + '\n')
     assert compared >= 3, 'too few probes could be compared'
-    # frames before S2 agree point-wise (a steep front shifted by a fraction of a step: 5 % of the range);
+    # frames before S2 agree point-wise within 1 % of the range (measured <= 0.28 %, court.py);
     # afterwards the excited fraction agrees
-    assert pre_err <= 0.05, pre_err
+    assert pre_err <= 0.01, pre_err
     assert frac_err <= 0.01, frac_err
 
 
