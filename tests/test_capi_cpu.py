@@ -68,6 +68,15 @@ def test_null_arguments_are_errors_not_crashes():
     assert L.fib_step(None, 0, 1) == -1
     assert L.fib_sync(None) == -1
     assert L.fib_destroy(None) == 0
+    # the round-2 entry points: a NULL context is an argument error before any CUDA call
+    n = C.c_size_t()
+    u = C.c_uint64()
+    assert L.fib_flush(None) == -1
+    assert L.fib_probe_watch(None, 0, 1, 1) == -1
+    assert L.fib_probe_fetch(None, None, 0, C.byref(n)) == -1
+    assert L.fib_count_below(None, 0, 0.0, 1.0, 0.2, 1e-3, C.byref(u), C.byref(u)) == -1
+    assert L.fib_set_rect_async(None, 0, 0, 1, 0, 1, None) == -1
+    assert 'NULL' in L.fib_last_error().decode()
 
 
 def test_no_cpu_fallback_without_gpu():
