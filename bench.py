@@ -96,20 +96,24 @@ def pinned_strips(tile, width):
     return out
 
 
-def upload_tiled(ctx, strips, row0, rows, width):
+def upload_tiled(ctx, strips, row0, rows, width, descending=False):
     """Strip-wise H2D upload (from pinned memory) of the mirror-tiled state for global rows
     [row0, row0+rows): every 512-row strip of every plane is one ENQUEUE-ONLY fib_set_rect_async, issued
-    top to bottom with all planes of a strip together, so that on an unsharded grid the library can step
-    block by block behind the copies (csrc/fib_capi.cu finish_upload_session)."""
-    nbytes = 0
+    block by block with all planes of a strip together, so that the library can step behind the copies
+    (csrc/fib_capi.cu finish_upload_session).  Top to bottom, or -- odd ranks of a sharded run -- bottom to
+    top, so that both shards of a seam begin or end their uploads there (fib_step_behind_upload)."""
+    pieces = []
     g = row0
     while g < row0 + rows:
         t, r = divmod(g, TILE)
         n = min(TILE - r, row0 + rows - g)
+        pieces.append((g, t, r, n))
+        g += n
+    nbytes = 0
+    for g, t, r, n in (reversed(pieces) if descending else pieces):
         for name, pinned in strips.items():
             ctx.set_rect_async(name, g, 0, pinned[t & 1][r:r + n])
             nbytes += n * width * 4
-        g += n
     return nbytes
 
 
@@ -475,7 +479,7 @@ def main():
     d2h = 0
     barrier()
     t0 = time.perf_counter()
-    h2d = upload_tiled(ctx, strips, row0, rows, size)
+    h2d = upload_tiled(ctx, strips, row0, rows, size, descending=(world > 1 and rank % 2 == 1))
     with contextlib.redirect_stdout(sys.stderr):
         for i in model.run(None):
             if i % 10 == 9 or i == K - 1:                 # a frame every 10 iterations (fenton.py:184) + the last

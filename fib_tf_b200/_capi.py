@@ -88,6 +88,8 @@ _SIGNATURES = {
     'fib_masked_sum': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'fib_sync': (C.c_int, [_P]),
     'fib_flush': (C.c_int, [_P]),
+    'fib_upload_state': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'fib_step_behind_upload': (C.c_int, [_P, C.c_int]),
     'fib_timer_start': (C.c_int, [_P]),
     'fib_timer_stop': (C.c_int, [_P]),
     'fib_timer_ms': (C.c_int, [_P, _FP]),
@@ -317,6 +319,16 @@ class Context:
     def flush(self):
         """Launch the iterations the persistent path has deferred (enqueue only)."""
         check(lib().fib_flush(self._h))
+
+    def upload_state(self):
+        """(open, complete, direction, max_iters) of the pipelined upload in flight (set_rect_async)."""
+        a, b, d, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().fib_upload_state(self._h, C.byref(a), C.byref(b), C.byref(d), C.byref(m)))
+        return bool(a.value), bool(b.value), d.value, m.value
+
+    def step_behind_upload(self, n_iter):
+        """n_iter ODE iterations behind a complete pipelined upload; collective on NCCL shards."""
+        check(lib().fib_step_behind_upload(self._h, int(n_iter)))
 
     def timer_start(self):
         check(lib().fib_timer_start(self._h))

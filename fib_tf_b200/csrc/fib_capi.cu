@@ -154,12 +154,14 @@ struct fib_ctx {
   // run on their own stream; `arrivals` = {rows [row0, row_end) of EVERY plane are enqueued up to `ev`}.
   // Iterations stepped while such a session is open are deferred and then run block by block behind the
   // copies (finish_upload_session).
-  struct Arrival { int row_end; cudaEvent_t ev; };
+  struct Arrival { int d_end; cudaEvent_t ev; };   // d = rows counted from the edge the upload started at
   cudaStream_t up_stream = nullptr;
   cudaEvent_t ev_up_begin = nullptr;
   bool up_session = false;
   std::vector<Arrival> arrivals;
-  std::vector<int> up_front;          // per plane: rows [row0, up_front) enqueued
+  std::vector<int> up_front;          // per plane: the first up_front rows (from the starting edge) are enqueued
+  int up_dir = +1;                    // +1: top to bottom, -1: bottom to top (NCCL shards: odd ranks, see below)
+  bool pipeline_nccl = true;          // FIB_PIPELINE_NCCL=0: no upload sessions on NCCL-sharded contexts
   std::vector<cudaEvent_t> ev_pool;
   long long pipeline_min_cells = 1ll << 22;   // smaller grids: not worth it (FIB_PIPELINE_MIN_CELLS)
   int pipeline_block_rows = 1024;             // rows per block of the skewed schedule, at least (FIB_PIPELINE_BLOCK_ROWS)
@@ -466,6 +468,7 @@ static int create_resources(fib_ctx* c) {
   CU(cudaEventCreateWithFlags(&c->ev_up_begin, cudaEventDisableTiming));
   if (const char* e = getenv("FIB_PIPELINE_MIN_CELLS")) c->pipeline_min_cells = atoll(e);
   if (const char* e = getenv("FIB_PIPELINE_BLOCK_ROWS")) c->pipeline_block_rows = max(atoi(e), 1);
+  if (const char* e = getenv("FIB_PIPELINE_NCCL")) c->pipeline_nccl = atoi(e) != 0;
   CU(cudaEventCreateWithFlags(&c->ev_snap_ready, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_snap_done, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_start));
@@ -737,26 +740,33 @@ static int set_rect_impl(fib_ctx* c, int var, int r0, int r1, int c0, int c1, co
     // A full-width block that continues this plane's upload frontier (or starts one at the first row) of a
     // large unsharded grid goes to the upload stream: iterations stepped before anything looks at the
     // result then run block by block BEHIND the copies instead of after them (finish_upload_session).
-    const bool eligible = !c->comm && c->g.rows == c->g.H && c0 == 0 && c1 == c->g.W && c->watch_var < 0 &&
-                          (long long)c->g.rows * c->g.W >= c->pipeline_min_cells;
-    if (eligible && !c->pending && (c->up_session ? r0 == c->up_front[var] : r0 == c->g.row0)) {
+    // On an NCCL shard the block order may also run bottom to top (odd ranks do, so that both shards of a seam
+    // either begin or end there: fib_step_behind_upload).
+    const bool eligible = (c->comm ? c->pipeline_nccl : c->g.rows == c->g.H) && c0 == 0 && c1 == c->g.W &&
+                          c->watch_var < 0 && (long long)c->g.rows * c->g.W >= c->pipeline_min_cells;
+    const int row_end = c->g.row0 + c->g.rows;
+    const int dir = c->up_session ? c->up_dir : (r0 == c->g.row0 ? +1 : (r1 == row_end && c->comm ? -1 : 0));
+    const int dlo = dir > 0 ? r0 - c->g.row0 : row_end - r1, dhi = dir > 0 ? r1 - c->g.row0 : row_end - r0;
+    if (eligible && dir != 0 && !c->pending && dlo == (c->up_session ? c->up_front[var] : 0)) {
       if (!c->up_session) {
         const int pr = preload_kernels(c);
         if (pr) return pr;                                       // (allocation failures only)
+        CU(wait_comm(c));
         CU(cudaEventRecord(c->ev_up_begin, c->stream));          // after everything stepped so far
         CU(cudaStreamWaitEvent(c->up_stream, c->ev_up_begin, 0));
         if (c->snap_pending) CU(cudaStreamWaitEvent(c->up_stream, c->ev_snap_done, 0));
-        c->up_front.assign(c->nvars, c->g.row0);
+        c->up_front.assign(c->nvars, 0);
+        c->up_dir = dir;
         c->up_session = true;
       }
       float* dst = owned_rows(c, var) + (size_t)(r0 - c->g.row0) * c->g.pitch;
       CU(cudaMemcpy2DAsync(dst, c->g.pitch * sizeof(float), host, (size_t)c->g.W * sizeof(float),
                            (size_t)c->g.W * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, c->up_stream));
-      c->up_front[var] = r1;
-      int done = r1;
+      c->up_front[var] = dhi;
+      int done = dhi;
       for (int f : c->up_front) done = min(done, f);
-      const int had = c->arrivals.empty() ? c->g.row0 : c->arrivals.back().row_end;
-      if (done - had >= c->pipeline_block_rows || (done > had && done == c->g.row0 + c->g.rows)) {
+      const int had = c->arrivals.empty() ? 0 : c->arrivals.back().d_end;
+      if (done - had >= c->pipeline_block_rows || (done > had && done == c->g.rows)) {
         cudaEvent_t ev = nullptr;
         if (!c->ev_pool.empty()) {
           ev = c->ev_pool.back();
@@ -1065,16 +1075,18 @@ static bool op_writes_x(const fib_ctx* c, int op) { return !(c->cfg.model == FIB
 
 // ---- NCCL halo exchange of buffer `buf` (rows just written), on `st` ------------------------
 // fuse == 2: kFuseHalo rows of every plane of buffer set `b` (rows are pitch-contiguous)
-static int nccl_exchange_fused(fib_ctx* c, int b, cudaStream_t st) {
+// `sides`: bit 0 = the seam with rank - 1 (above), bit 1 = the seam with rank + 1 (below)
+enum { kSeamUp = 1, kSeamDown = 2, kSeamBoth = 3 };
+static int nccl_exchange_fused(fib_ctx* c, int b, cudaStream_t st, int sides) {
   const size_t P = c->g.pitch, n = (size_t)kFuseHalo * P;
   NC(g_nccl.GroupStart());
   for (int v = 0; v < 4; ++v) {
     float* buf = c->fx[b][v];
-    if (c->rank > 0) {
+    if (c->rank > 0 && (sides & kSeamUp)) {
       NC(g_nccl.Send(buf + n, n, kNcclFloat, c->rank - 1, c->comm, st));
       NC(g_nccl.Recv(buf, n, kNcclFloat, c->rank - 1, c->comm, st));
     }
-    if (c->rank + 1 < c->nranks) {
+    if (c->rank + 1 < c->nranks && (sides & kSeamDown)) {
       NC(g_nccl.Send(buf + (size_t)c->g.rows * P, n, kNcclFloat, c->rank + 1, c->comm, st));
       NC(g_nccl.Recv(buf + (size_t)c->g.rows * P + n, n, kNcclFloat, c->rank + 1, c->comm, st));
     }
@@ -1083,16 +1095,16 @@ static int nccl_exchange_fused(fib_ctx* c, int b, cudaStream_t st) {
   return 0;
 }
 
-static int nccl_exchange(fib_ctx* c, int b, cudaStream_t st) {
-  if (c->fuse == 2) return nccl_exchange_fused(c, b, st);
+static int nccl_exchange(fib_ctx* c, int b, cudaStream_t st, int sides = kSeamBoth) {
+  if (c->fuse == 2) return nccl_exchange_fused(c, b, st, sides);
   float* buf = c->x[b];
   const size_t W = c->g.W, P = c->g.pitch;
   NC(g_nccl.GroupStart());
-  if (c->rank > 0) {
+  if (c->rank > 0 && (sides & kSeamUp)) {
     NC(g_nccl.Send(buf + P, W, kNcclFloat, c->rank - 1, c->comm, st));
     NC(g_nccl.Recv(buf, W, kNcclFloat, c->rank - 1, c->comm, st));
   }
-  if (c->rank + 1 < c->nranks) {
+  if (c->rank + 1 < c->nranks && (sides & kSeamDown)) {
     NC(g_nccl.Send(buf + (size_t)c->g.rows * P, W, kNcclFloat, c->rank + 1, c->comm, st));
     NC(g_nccl.Recv(buf + (size_t)(c->g.rows + 1) * P, W, kNcclFloat, c->rank + 1, c->comm, st));
   }
@@ -1452,7 +1464,19 @@ static int step_now(fib_ctx* c, int op, int n_iter) {
 // gets every launch exactly once and in order, a launch reads only rows its predecessors have brought to
 // its time level, and block j's launches wait for block j's copies only -- the same arithmetic on the
 // same values as stepping after the whole upload, so the result is bit-identical.
-static int finish_upload_session(fib_ctx* c, int n) {
+// iterations a session can still defer: launch l of the first block ends at row a_0 - nb (l + 1) > 0
+static int upload_room_iters(const fib_ctx* c) {
+  if (!c->up_session || c->arrivals.empty()) return 0;
+  const int nl = substeps_of(c, FIB_OP_ODE) / c->fuse;
+  return max((c->arrivals[0].d_end / c->fuse - 3) / max(nl, 1), 0);
+}
+
+// NCCL shards (`comm_skew`, only through fib_step_behind_upload -- every rank must take the same path): the
+// skew starts at the edge the upload started at.  Even ranks upload top to bottom and odd ranks bottom to top,
+// so both shards of a seam either BEGIN there (their first blocks advance launch by launch in lock step,
+// exchanging the seam's halo rows after every launch) or END there (the same for their last blocks); the
+// blocks in between need no exchange at all.
+static int finish_upload_session(fib_ctx* c, int n, bool comm_skew = false) {
   c->up_session = false;
   std::vector<fib_ctx::Arrival> blocks;
   blocks.swap(c->arrivals);
@@ -1461,33 +1485,47 @@ static int finish_upload_session(fib_ctx* c, int n) {
   };
   const int op = FIB_OP_ODE;
   const int nb = c->fuse, nl = substeps_of(c, op) / c->fuse, L = n * nl;
-  const int row0 = c->g.row0, rows = c->g.rows;
-  bool skew = n > 0 && blocks.size() > 1 && blocks.back().row_end == row0 + rows && c->persist != 1 &&
-              blocks[0].row_end - row0 > nb * (L + 2);
-  for (size_t j = 1; skew && j < blocks.size(); ++j) skew = blocks[j].row_end - blocks[j - 1].row_end > 2 * nb;
+  const int rows = c->g.rows, dir = c->up_dir;
+  const bool sharded = c->comm != nullptr;
+  bool skew = n > 0 && blocks.size() > 1 && blocks.back().d_end == rows && c->persist != 1 &&
+              blocks[0].d_end > nb * (L + 2) && (!sharded || comm_skew);
+  for (size_t j = 1; skew && j < blocks.size(); ++j) skew = blocks[j].d_end - blocks[j - 1].d_end > 2 * nb;
   if (!skew) {
     if (!blocks.empty()) CU(cudaStreamWaitEvent(c->stream, blocks.back().ev, 0));
     release();
+    if (comm_skew) return fail(FIB_E_STATE, "fib_step_behind_upload: this upload cannot be pipelined (fib_upload_state)");
     return n ? step_now(c, op, n) : 0;
   }
+  // the seams of this shard, named by where the upload began
+  const int side_start = dir > 0 ? kSeamUp : kSeamDown, side_end = dir > 0 ? kSeamDown : kSeamUp;
+  const bool has_up = sharded && c->rank > 0, has_down = sharded && c->rank + 1 < c->nranks;
+  const bool seam_start = dir > 0 ? has_up : has_down, seam_end = dir > 0 ? has_down : has_up;
+  if (sharded) CU(wait_comm(c));
   const int cur0 = c->cur;
   const bool flips = op_writes_x(c, op);
   int r = 0;
   for (size_t j = 0; j < blocks.size() && !r; ++j) {
     CU(cudaStreamWaitEvent(c->stream, blocks[j].ev, 0));
-    const bool last = j + 1 == blocks.size();
+    const bool first = j == 0, last = j + 1 == blocks.size();
+    // the seam's halo rows of the state just uploaded
+    if (first && seam_start) r = nccl_exchange(c, cur0, c->stream, side_start);
+    if (!r && last && seam_end) r = nccl_exchange(c, cur0, c->stream, side_end);
     for (int l = 0; l < L && !r; ++l) {
-      const int lo = j == 0 ? 0 : blocks[j - 1].row_end - row0 - nb * (l + 1);
-      const int hi = last ? rows : blocks[j].row_end - row0 - nb * (l + 1);
+      const int dlo = first ? 0 : blocks[j - 1].d_end - nb * (l + 1);
+      const int dhi = last ? rows : blocks[j].d_end - nb * (l + 1);
+      const int lo = dir > 0 ? dlo : rows - dhi, hi = dir > 0 ? dhi : rows - dlo;
       c->cur = cur0 ^ ((flips && (l & 1)) ? 1 : 0);
       r = launch_substep(c, op, (l % nl) * c->fuse, lo, hi - lo);
-      if (!r && (l + 1) % nl == 0 && c->watch_var >= 0 && c->watch_row - row0 >= lo && c->watch_row - row0 < hi) {
+      if (!r && flips && first && seam_start) r = nccl_exchange(c, c->cur ^ 1, c->stream, side_start);
+      if (!r && flips && last && seam_end) r = nccl_exchange(c, c->cur ^ 1, c->stream, side_end);
+      if (!r && (l + 1) % nl == 0 && c->watch_var >= 0 && c->watch_row - c->g.row0 >= lo && c->watch_row - c->g.row0 < hi) {
         if (flips) c->cur ^= 1;
         r = record_probe(c, op);        // the watched cell's row has finished this iteration
       }
     }
   }
   c->cur = cur0 ^ ((flips && (L & 1)) ? 1 : 0);
+  if (sharded && !r) c->halo_dirty = false;
   release();
   return r;
 }
@@ -1508,12 +1546,10 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
   if (!c->comm && c->g.rows != c->g.H)
     return fail(FIB_E_STATE, "a row shard needs fib_comm_init (multi-process) or fib_step_group");
   if (!c->comm && c->persist < 0) decide_persist(c);
-  if (c->up_session && op == FIB_OP_ODE && c->persist != 1 && !c->arrivals.empty()) {
+  if (c->up_session && !c->comm && op == FIB_OP_ODE && c->persist != 1 && !c->arrivals.empty()) {
     // an upload is still in flight: count the iterations, run them behind the copies when something looks
     // (finish_upload_session); at most as many as the first block's height allows
-    const int nl = substeps_of(c, op) / c->fuse;
-    const int room = (c->arrivals[0].row_end - c->g.row0) / c->fuse - 2 - (c->pending + n_iter) * nl;
-    if (room > 0) {
+    if (c->pending + n_iter <= upload_room_iters(c)) {
       c->pending += n_iter;
       return 0;
     }
@@ -1532,6 +1568,35 @@ extern "C" int fib_step(fib_ctx* c, int op, int n_iter) {
   }
   FLUSH(c);
   return step_now(c, op, n_iter);
+}
+
+// What a caller has to know before it asks for fib_step_behind_upload on NCCL shards (every rank must take the
+// same decision, so the host side reduces these over the ranks first: fib_tf_b200/ionic.py run()).
+extern "C" int fib_upload_state(const fib_ctx* c, int* open, int* complete, int* direction, int* max_iters) {
+  if (!c || !open || !complete || !direction || !max_iters) return fail(FIB_E_ARG, "NULL argument");
+  *open = c->up_session ? 1 : 0;
+  *complete = (c->up_session && !c->arrivals.empty() && c->arrivals.back().d_end == c->g.rows && c->arrivals.size() > 1) ? 1 : 0;
+  *direction = c->up_session ? c->up_dir : 0;
+  *max_iters = upload_room_iters(c);
+  return 0;
+}
+
+// n_iter ODE iterations behind a complete pipelined upload, NOW (enqueue only).  On NCCL shards this is a
+// collective with its own exchange pattern: all ranks call it, with the same n_iter, after agreeing that every
+// rank has a complete upload whose direction is top-to-bottom on even and bottom-to-top on odd ranks.
+extern "C" int fib_step_behind_upload(fib_ctx* c, int n_iter) {
+  if (!c) return fail(FIB_E_ARG, "ctx is NULL");
+  if (n_iter < 1) return fail(FIB_E_ARG, "n_iter < 1");
+  DevGuard dg(c->cfg.device);
+  if (!c->up_session) return fail(FIB_E_STATE, "fib_step_behind_upload: no pipelined upload is open");
+  if (c->pending) return fail(FIB_E_STATE, "fib_step_behind_upload: iterations are already deferred on this context");
+  if (c->comm && ((c->rank % 2 == 0) != (c->up_dir > 0)))
+    return fail(FIB_E_STATE, "fib_step_behind_upload: rank %d must upload %s", c->rank,
+                c->rank % 2 == 0 ? "top to bottom" : "bottom to top");
+  if (n_iter > upload_room_iters(c))
+    return fail(FIB_E_STATE, "fib_step_behind_upload: at most %d iterations fit behind this upload", upload_room_iters(c));
+  if (!c->comm && c->persist < 0) decide_persist(c);
+  return finish_upload_session(c, n_iter, c->comm != nullptr);
 }
 
 // ---- in-process shard group: lock-step, device-to-device halo copies ------------------------

@@ -29,6 +29,10 @@ Extra, optional config keys (all default to the reference's behaviour):
                  to twice that many iterations late, with the reference's arguments; 1 = read it
                  back every iteration like the reference)
 
+    upload_window  distributed runs: how many of run()'s first iterations may run behind a pipelined upload
+                 (fib_set_rect_async blocks, even ranks top to bottom, odd ranks bottom to top; default 10,
+                 0 = never; the ranks agree on the number at the start of run())
+
 Collective calls under config['distributed'] (every rank must make them, in the same order):
 define(), run() (each iteration), fire_op(), image(), pot().eval() / _State[..].eval(),
 var[r, c].eval(), masked_image_mean(), excitable_fraction(), close().  cl_observer callbacks run on
@@ -230,6 +234,39 @@ class IonicModel:
         self._ctx = ctx
         return ctx
 
+    # The context, with one twist for NCCL shards: iterations that run() has counted to run behind a
+    # pipelined upload (csrc finish_upload_session) are executed by the first thing that touches the context
+    # -- every such touch is a collective call under config['distributed'], and every rank holds the same
+    # count, so all ranks issue fib_step_behind_upload at the same point of their call sequence.
+    @property
+    def _ctx(self):
+        d = self.__dict__
+        n = d.get('_behind', 0)
+        if n:
+            d['_behind'], d['_behind_limit'] = 0, 0
+            d['_ctx_obj'].step_behind_upload(n)
+        return d.get('_ctx_obj')
+
+    @_ctx.setter
+    def _ctx(self, value):
+        self.__dict__['_ctx_obj'] = value
+
+    def _agree_on_upload_window(self, im, batch):
+        """How many of run()'s first iterations all ranks will run behind their pipelined uploads (0: none).
+        Collective: the answer is the minimum over the ranks, so one rank without a complete upload of the right
+        direction (even ranks top to bottom, odd ranks bottom to top) switches it off for everybody."""
+        if self._nranks == 1 or im or batch <= 1 or self.ode_op(0) != 0:
+            return 0
+        import torch
+        import torch.distributed as dist
+        open_, complete, direction, room = self.__dict__['_ctx_obj'].upload_state()
+        ok = open_ and complete and direction == (1 if self._rank % 2 == 0 else -1)
+        want = min(room, self.samples, int(self.__dict__.get('upload_window', 10))) if ok else 0
+        dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+        t = torch.tensor([want], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     def _local_full(self, value):
         """[rows, W] fp32 array filled with `value` for this shard's rows."""
         return np.full([self._rows, self.width], value, dtype=np.float32)
@@ -328,11 +365,18 @@ class IonicModel:
                     crossing(k, self._normalise(float(raw)) * w)
             del unread[:n]
 
+        self._behind, self._behind_limit = 0, self._agree_on_upload_window(im, batch)
+        self._upload_window_used = self._behind_limit
         if ring:
             self._ctx.probe_watch(self._pot_name, prow, pcol)
         try:
             for i in range(self.samples):
-                self._ctx.step(self.ode_op(i), 1)
+                if i < self._behind_limit:
+                    self._behind += 1                        # runs behind the upload: see the _ctx property
+                    if self._behind == self._behind_limit:
+                        self._ctx                            # noqa: B018 (the window is full: go)
+                else:
+                    self._ctx.step(self.ode_op(i), 1)
                 yield i
                 if ring:
                     unread.append(i)

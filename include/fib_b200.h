@@ -171,6 +171,17 @@ int fib_court_inter(fib_ctx *ctx, const float *v_host, size_t n, float *out_host
 int fib_step(fib_ctx *ctx, int op, int n_iter);
 /* launch whatever fib_step has deferred (enqueue only, no synchronisation) */
 int fib_flush(fib_ctx *ctx);
+/* Pipelined uploads on NCCL shards.  An unsharded context steps behind its upload by itself (fib_set_rect_async);
+ * on NCCL shards the skewed schedule needs its own exchange pattern, so it is explicit and COLLECTIVE: every rank
+ * uploads its shard block by block -- even ranks top to bottom, odd ranks bottom to top, so that both shards of a
+ * seam either begin or end there -- then all ranks agree (host side, e.g. an all-reduce of fib_upload_state's
+ * answers: open, complete, direction = +1 / -1, the number of iterations that fit) and call
+ * fib_step_behind_upload with the same n_iter.  First blocks advance in lock step with the neighbour that also
+ * begins at that seam, exchanging the seam's halo rows after every launch; last blocks likewise; the blocks in
+ * between run behind their copies without any exchange.  Without the explicit call a sharded context simply
+ * waits for its upload (fib_step).  Bit-identical to upload-then-step (tests/dist_parity.py). */
+int fib_upload_state(const fib_ctx *ctx, int *open, int *complete, int *direction, int *max_iters);
+int fib_step_behind_upload(fib_ctx *ctx, int n_iter);
 /* lock-step stepping of several shards living in ONE process (row-adjacent, ctxs[0] on top):
  * halo rows are exchanged device-to-device after every time step.  Used to emulate the
  * multi-GPU decomposition on one device and for single-process multi-GPU. */

@@ -13,7 +13,73 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+def pipelined_upload_cases(CLASSES, base, local, rank, world):
+    """Every rank uploads its shard block by block (even ranks top to bottom, odd ranks bottom to top) and run()
+    steps its first iterations BEHIND the copies (fib_step_behind_upload: seam exchanges after every launch of
+    the first / last block, none in between).  State and probe ring must equal upload-then-step, unsharded."""
+    from fib_tf_b200 import _capi
+    ok = True
+    H, W, block = 160 * world, 200, 40
+    for kind, extra, window, iters in (('fenton4v', {'steps_per_launch': 2}, 3, 6), ('fenton4v', {'steps_per_launch': 1}, 3, 5),
+                                       ('br', {'cheby': True, 'skip': True}, 6, 8), ('court_ultra', {'ultra_slow': True}, 20, 30)):
+        cfg = dict(base, width=W, height=H, **extra)
+        m = CLASSES[kind](dict(cfg, distributed=True, device=local, upload_window=window))
+        dt_iter = None
+        models = [m]
+        if rank == 0:
+            models.append(CLASSES[kind](dict(cfg, device=local, steps_per_launch=1, persist=False)))
+        for mm in models:
+            mm.add_hole_to_phase_field(90, 60, 17)
+            mm.define()
+            mm.duration = iters * mm.dt_per_step * mm.dt + 1e-9
+        rng = np.random.default_rng(1234)                      # the same planes on every rank
+        names = m._ctx.var_names
+        full = {}
+        for v in names:
+            base_v = m._State[v].eval()                        # (collective) the model's own initial state ...
+            noise = rng.uniform(-1.0, 1.0, (H, W)).astype(np.float32)
+            full[v] = (base_v + np.float32(0.02) * noise * np.maximum(np.abs(base_v), np.float32(1e-3))).astype(np.float32)
+        row0, rows = m._row0, m._rows
+        pinned = {v: _capi.pinned_empty((rows, W)) for v in names}
+        for v in names:
+            pinned[v][...] = full[v][row0:row0 + rows]
+        starts = list(range(0, rows, block))
+        for r in (starts if rank % 2 == 0 else reversed(starts)):       # block-major, every plane of a block
+            for v in names:
+                m._ctx_obj.set_rect_async(v, row0 + r, 0, pinned[v][r:min(r + block, rows)])
+        if rank == 0:
+            for v in names:
+                models[1]._ctx.set_state(v, full[v])
+        seen = []
+        m.cl_observer = lambda i, cl: seen.append((i, cl))
+        for i in m.run(None, block=False):
+            pass
+        used = m._upload_window_used
+        if rank == 0:
+            models[1]._ctx.step(0, iters)
+        for v in names:
+            got = m._State[v].eval()
+            if rank == 0:
+                same = np.array_equal(got, models[1]._State[v].eval(), equal_nan=True)
+                ok &= same
+                if not same:
+                    print('MISMATCH pipelined %s %s' % (kind, v))
+        if used != window:
+            ok = False
+            print('pipelined %s: window %d was not used (%d)' % (kind, window, used))
+        if rank == 0:
+            print('%-12s %s pipelined upload, %d iterations behind the copies, %d ranks: sharded == unsharded: %s'
+                  % (kind, extra, used, world, ok), flush=True)
+        for mm in models:
+            mm.close()
+        for v in names:
+            _capi.pinned_free(pinned[v])
+    return ok
+
+
 def main():
+    os.environ.setdefault('FIB_PIPELINE_MIN_CELLS', '0')
+    os.environ.setdefault('FIB_PIPELINE_BLOCK_ROWS', '40')
     from cuda_adapter import CLASSES
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -76,6 +142,7 @@ def main():
             print('%-12s %s %d ranks: sharded == unsharded: %s' % (kind, extra, world, ok), flush=True)
         for m in models:
             m.close()
+    ok &= pipelined_upload_cases(CLASSES, base, local, rank, world)
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
