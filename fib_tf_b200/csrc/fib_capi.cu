@@ -2061,5 +2061,14 @@ extern "C" int fib_comm_init(fib_ctx* c, int nranks, int rank, const void* id128
   c->rank = rank;
   c->halo_dirty = true;
   c->persist = 0;          // the persistent kernel is for unsharded grids
+  // Bring up the connections of every exchange pattern now, outside anybody's timed region: both seams in one
+  // group (the per-step exchange) and each seam on its own (fib_step_behind_upload).  The halo rows this moves
+  // are refreshed before their first use (halo_dirty).  Collective like the rest of this call; the one-seam
+  // exchanges pair rank r's lower seam with rank r+1's upper one, a chain that starts at rank 0.
+  int w = nccl_exchange(c, c->cur, c->stream, kSeamBoth);
+  if (!w) w = nccl_exchange(c, c->cur, c->stream, kSeamUp);
+  if (!w) w = nccl_exchange(c, c->cur, c->stream, kSeamDown);
+  if (w) return w;
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
