@@ -150,10 +150,11 @@ struct fib_ctx {
   unsigned long long* pmail = nullptr;   // edge-row mailbox of the persistent kernel, words {value, step number}
   unsigned pbase = 0;
   int pending = 0;                    // ODE iterations accepted by fib_step but not launched yet (see flush_pending)
-  // Pipelined upload (fib_set_rect_async of full-width row blocks, top to bottom, every plane): the copies
-  // run on their own stream; `arrivals` = {rows [row0, row_end) of EVERY plane are enqueued up to `ev`}.
-  // Iterations stepped while such a session is open are deferred and then run block by block behind the
-  // copies (finish_upload_session).
+  // Pipelined upload (fib_set_rect_async of full-width row blocks, in order from one edge of the shard, every
+  // plane): the copies run on their own stream; `arrivals` = {the first d_end rows, counted from that edge, of
+  // EVERY plane are enqueued up to `ev`}.  Iterations stepped while such a session is open are deferred
+  // (unsharded contexts) or asked for explicitly (NCCL shards, fib_step_behind_upload) and then run block by
+  // block behind the copies (finish_upload_session).
   struct Arrival { int d_end; cudaEvent_t ev; };   // d = rows counted from the edge the upload started at
   cudaStream_t up_stream = nullptr;
   cudaEvent_t ev_up_begin = nullptr;

@@ -1,7 +1,8 @@
 """torchrun --nproc-per-node N tests/dist_parity.py : on N GPUs, the NCCL row-sharded run (one
 process per GPU, halo rows over ncclSend/ncclRecv) must be BIT-IDENTICAL to the unsharded run
 that rank 0 performs on its own GPU.  All three model families, with a phase field and a
-stimulus that straddles the seams."""
+stimulus that straddles the seams; a rank-local host write; two time steps per launch; and the
+pipelined upload behind NCCL shards (fib_step_behind_upload through IonicModel.run())."""
 import os
 import sys
 
