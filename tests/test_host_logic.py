@@ -143,3 +143,37 @@ def test_halo_plan_two_rows_deep_for_two_steps_per_launch():
     assert len(plans[0]) == 1 and len(plans[-1]) == 1 and all(len(p) == 2 for p in plans[1:-1])
     with pytest.raises(ValueError):
         halo_plan(5, 4, 3, depth=2)                                       # a 1-row shard cannot
+
+
+def test_bench_upload_order_is_block_major_and_reversible():
+    """bench.py uploads every plane of a 512-row strip before the next strip (so the library can step behind the
+    copies), top to bottom -- or bottom to top on the odd ranks of a sharded run; either way each row of each plane
+    exactly once, partial strips at the shard's edges included."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def set_rect_async(self, name, r0, c0, block):
+            self.calls.append((name, r0, block.shape[0]))
+
+    W = 8
+    strips = {v: [np.zeros((bench.TILE, W), np.float32), np.ones((bench.TILE, W), np.float32)] for v in 'UVWS'}
+    row0, rows = 700, 1500                                  # starts and ends inside a strip
+    up, down = Rec(), Rec()
+    n_up = bench.upload_tiled(up, strips, row0, rows, W)
+    n_down = bench.upload_tiled(down, strips, row0, rows, W, descending=True)
+    assert n_up == n_down == 4 * rows * W * 4
+    for rec, starts in ((up, [700, 1024, 1536, 2048]), (down, [2048, 1536, 1024, 700])):
+        assert [c[1] for c in rec.calls[::4]] == starts
+        for k in range(0, len(rec.calls), 4):               # the four planes of a strip together
+            assert [c[0] for c in rec.calls[k:k + 4]] == list('UVWS') and len({c[1:] for c in rec.calls[k:k + 4]}) == 1
+        covered = sorted((c[1], c[1] + c[2]) for c in rec.calls if c[0] == 'U')
+        assert covered[0][0] == row0 and covered[-1][1] == row0 + rows
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
